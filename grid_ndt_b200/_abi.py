@@ -1,0 +1,106 @@
+"""ctypes / numpy mirror of include/gndt.h (record layouts, enums, params struct).
+
+Kept in one place so that the product binding (grid_ndt_b200.builder) and the test-side
+oracle wrapper (oracle/oracle.py) agree byte-for-byte with the C header.
+"""
+import ctypes as C
+
+import numpy as np
+
+GNDT_ABI_VERSION = 1
+GNDT_OK, GNDT_ERR_INVALID_ARG, GNDT_ERR_CUDA, GNDT_ERR_CAPACITY, GNDT_ERR_STATE, GNDT_ERR_INTERNAL = 0, -1, -2, -3, -4, -5
+GNDT_MEM_HOST, GNDT_MEM_DEVICE = 0, 1
+GNDT_DEMAND_SLOPE, GNDT_DEMAND_TRUE = 0, 1
+GNDT_MAX_INDEX = 32767
+GNDT_MAX_POINTS = 1 << 30
+
+F_FITTED, F_SLOPE, F_UP, F_DOWN = 0x01, 0x02, 0x04, 0x08
+F_REACH_L, F_REACH_R, F_REACH_F, F_REACH_B = 0x10, 0x20, 0x40, 0x80
+F_REACH_ALL = 0xF0
+F_COLUMN_HEAD = 0x100
+
+STAGE_NAMES = ("key", "sort", "reduce", "label", "edges", "total", "h2d", "reserved")
+N_STAGES = 8
+
+
+class Params(C.Structure):
+    """gndt_params (include/gndt.h)."""
+
+    _fields_ = [
+        ("grid_len", C.c_float),
+        ("z_len", C.c_float),
+        ("slope_interval", C.c_float),
+        ("demand", C.c_int32),
+        ("min_points", C.c_int32),
+        ("rough_max", C.c_float),
+        ("angle_max_deg", C.c_float),
+        ("reach_height", C.c_float),
+        ("origin_is_first_point", C.c_int32),
+        ("origin", C.c_float * 3),
+        ("normalize_cov", C.c_int32),
+        ("tile_lo", C.c_int32),
+        ("tile_hi", C.c_int32),
+        ("max_voxels", C.c_uint64),
+    ]
+
+
+def default_params(grid_len=0.5, z_len=0.1, slope_interval=0.08, demand="slope", **kw) -> Params:
+    """Reference defaults: TwoDmap map2D(0.5,0.1) (src/receiver.cpp:35), MINPOINTSIZE 3
+    (include/map2D.h:28), RobotSphere thresholds (include/robot.h:38-46).  Floats are
+    rounded double->float exactly like the ROS param path does (receiver.cpp:260-269)."""
+    p = Params()
+    p.grid_len = np.float32(grid_len)
+    p.z_len = np.float32(z_len)
+    p.slope_interval = np.float32(slope_interval)
+    p.demand = {"slope": GNDT_DEMAND_SLOPE, "true": GNDT_DEMAND_TRUE}[demand] if isinstance(demand, str) else int(demand)
+    p.min_points = 3
+    p.rough_max = 100.0
+    p.angle_max_deg = 30.0
+    p.reach_height = np.float32(0.15)
+    p.origin_is_first_point = 1
+    p.normalize_cov = 0
+    p.tile_lo = 0
+    p.tile_hi = 0
+    p.max_voxels = 0
+    for k, v in kw.items():
+        if k == "origin":
+            for i in range(3):
+                p.origin[i] = np.float32(v[i])
+        else:
+            setattr(p, k, v)
+    return p
+
+
+VOXEL_DTYPE = np.dtype(
+    [
+        ("sx", "<i4"), ("sy", "<i4"), ("sz", "<i4"),
+        ("count", "<u4"), ("first_index", "<u4"),
+        ("mean", "<f4", (3,)), ("scatter", "<f4", (6,)), ("evals", "<f4", (3,)),
+        ("normal", "<f4", (3,)), ("rough", "<f4"), ("flags", "<u4"), ("reserved", "<u4", (2,)),
+    ]
+)
+SLOPE_DTYPE = np.dtype(
+    [
+        ("sx", "<i4"), ("sy", "<i4"), ("sz", "<i4"),
+        ("mean", "<f4", (3,)), ("normal", "<f4", (3,)), ("rough", "<f4"),
+        ("flags", "<u4"), ("voxel", "<u4"),
+    ]
+)
+COLUMN_DTYPE = np.dtype(
+    [
+        ("sx", "<i4"), ("sy", "<i4"), ("first_index", "<u4"),
+        ("voxel_begin", "<u4"), ("voxel_count", "<u4"), ("slope_count", "<u4"),
+    ]
+)
+assert VOXEL_DTYPE.itemsize == 96 and SLOPE_DTYPE.itemsize == 48 and COLUMN_DTYPE.itemsize == 24
+
+
+class Counts(C.Structure):
+    """gndt_counts_t (include/gndt.h)."""
+
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_input", "n_binned", "n_dropped", "n_outside_tile",
+        "n_columns", "n_voxels", "n_fitted", "n_slopes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -1,0 +1,247 @@
+/*
+ * gndt.h — C ABI of the B200-native grid-NDT map builder (libgndt.so).
+ *
+ * This is the drop-in boundary for the map-construction path of daysun/grid_ndt.
+ * The reference has no FFI/plugin interface: the boundary there is a pair of
+ * in-process C++ call sites and four public containers.  Every entry point below
+ * cites the reference interface it replaces (paths relative to the reference
+ * tree).  The host adapter that turns the tables returned here back into the
+ * reference's `TwoDmap::map_cell / map_xy / morton_list` objects lives in
+ * adapter/gndt_twodmap_adapter.h and is NOT part of this ABI.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions, no C++/torch types cross this boundary
+ *   - every function returns a gndt_status (0 = ok, negative = error) unless noted
+ *   - the caller owns all host buffers; the library owns all device memory
+ *   - one handle is used from one thread at a time; all device work is ordered on
+ *     the stream passed in (a cudaStream_t cast to void*, NULL = default stream)
+ *   - there is no CPU fallback: without a CUDA device gndt_create fails with
+ *     GNDT_ERR_CUDA
+ */
+#ifndef GNDT_H
+#define GNDT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNDT_ABI_VERSION 1
+
+typedef enum gndt_status {
+  GNDT_OK = 0,
+  GNDT_ERR_INVALID_ARG = -1,  /* NULL pointer, bad stride, bad enum, n == 0 ...            */
+  GNDT_ERR_CUDA = -2,         /* a CUDA runtime call failed; see gndt_last_error            */
+  GNDT_ERR_CAPACITY = -3,     /* caller buffer too small / n exceeds GNDT_MAX_POINTS        */
+  GNDT_ERR_STATE = -4,        /* result queried before a successful gndt_build              */
+  GNDT_ERR_INTERNAL = -5      /* device-side consistency check tripped (watchdog)           */
+} gndt_status;
+
+/* where a caller buffer lives */
+typedef enum gndt_mem { GNDT_MEM_HOST = 0, GNDT_MEM_DEVICE = 1 } gndt_mem;
+
+/* `demand` string of the reference (src/receiver.cpp:256, include/map2D.h:630,644) */
+typedef enum gndt_demand { GNDT_DEMAND_SLOPE = 0, GNDT_DEMAND_TRUE = 1 } gndt_demand;
+
+#define GNDT_MAX_POINTS ((size_t)1 << 30) /* 30-bit tile-prefix words in the radix partition */
+#define GNDT_MAX_INDEX 32767              /* |nx|,|ny|,|nz| limit (Stopwatch.h:102-110 overflow) */
+
+/*
+ * Parameters.  Replaces: TwoDmap::TwoDmap(res,zres) + setLen/setZLen/setInterval
+ * (include/map2D.h:487-501), the `demand` ROS param (src/receiver.cpp:256),
+ * MINPOINTSIZE (include/map2D.h:28) and the RobotSphere thresholds
+ * (include/robot.h:38-46).  Floats must be passed already rounded the way the
+ * reference rounds them (ROS double param -> float).
+ */
+typedef struct gndt_params {
+  float grid_len;              /* setLen            : x-y cell edge, metres                 */
+  float z_len;                 /* setZLen           : z cell edge, metres                   */
+  float slope_interval;        /* setInterval       : layer-split threshold on mean.z       */
+  int32_t demand;              /* gndt_demand                                               */
+  int32_t min_points;          /* MINPOINTSIZE = 3                                          */
+  float rough_max;             /* RobotSphere::getRough()           = 100                   */
+  float angle_max_deg;         /* RobotSphere::getAngle()           = 30                    */
+  float reach_height;          /* RobotSphere::getReachableHeight() = 0.15f                 */
+  int32_t origin_is_first_point; /* 1: origin = point 0 and point 0 is not binned
+                                    (src/receiver.cpp:145,150); 0: use origin[] and bin all
+                                    points (changeCallback loop, src/receiver.cpp:189)      */
+  float origin[3];             /* setCloudFirst, used when origin_is_first_point == 0       */
+  int32_t normalize_cov;       /* 0 = un-normalised scatter (pcl::computeCovarianceMatrix);
+                                  1 = divide by n (computeCovarianceMatrixNormalized)       */
+  int32_t tile_lo;             /* multi-GPU x strip: keep columns with tile_lo <= cx <      */
+  int32_t tile_hi;             /*   tile_hi, cx = contiguous signed x index (sx>0?sx-1:sx). */
+                               /*   tile_lo >= tile_hi disables the filter (single GPU).    */
+  uint64_t max_voxels;         /* capacity of the device voxel table; 0 = number of points  */
+} gndt_params;
+
+/* Fill *p with the reference defaults (receiver.cpp:33-35 + robot.h + map2D.h:28). */
+void gndt_default_params(gndt_params *p);
+
+/*
+ * One occupied voxel = one OcNode of the reference (include/map2D.h:38-57) plus,
+ * when it is a surface, its Slope (include/map2D.h:136-146).  Fixed 96 bytes.
+ * Table order: ascending (cx, cy, cz) of the contiguous signed indices, i.e. all
+ * voxels of one x-y column are adjacent and sorted bottom-to-top.
+ */
+typedef struct gndt_voxel {
+  int32_t sx, sy, sz;      /* signed NON-ZERO cell indices (map2D.h:965-973); quadrant
+                              letter = signs: A(+,+) B(+,-) C(-,+) D(-,-)                */
+  uint32_t count;          /* points binned into the voxel (OcNode::N once >= min_points) */
+  uint32_t first_index;    /* cloud index of the first point that fell into the voxel     */
+  float mean[3];           /* OcNode::xyz_centroid; zeros when count < min_points         */
+  float scatter[6];        /* xx,xy,xz,yy,yz,zz of OcNode::covariance_matrix              */
+  float evals[3];          /* eigenvalues of the scatter, ascending                       */
+  float normal[3];         /* unit eigenvector of evals[0] (sign arbitrary)               */
+  float rough;             /* Slope::rough = evals[0], 0 -> 0.01 (map2D.h:131-132)        */
+  uint32_t flags;          /* GNDT_F_*                                                    */
+  uint32_t reserved[2];
+} gndt_voxel;
+
+#define GNDT_F_FITTED 0x01u   /* count >= min_points: mean/scatter/eigen valid            */
+#define GNDT_F_SLOPE 0x02u    /* a Slope object exists for this voxel (map2D.h:630-660)   */
+#define GNDT_F_UP 0x04u       /* isSlope()'s `up`  (slope demand) / countUp() (true)      */
+#define GNDT_F_DOWN 0x08u     /* isSlope()'s `down`                                       */
+#define GNDT_F_REACH_L 0x10u  /* a reachable Slope exists in the left  neighbour cell     */
+#define GNDT_F_REACH_R 0x20u  /*   "      right   (countLRFB/countReachable,              */
+#define GNDT_F_REACH_F 0x40u  /*   "      forward  map2D.h:197-296)                       */
+#define GNDT_F_REACH_B 0x80u  /*   "      back                                            */
+#define GNDT_F_COLUMN_HEAD 0x100u /* first voxel of its x-y column (one Cell per column)  */
+
+/* One Slope (include/map2D.h:136-146) — the compacted subset the planner reads. */
+typedef struct gndt_slope {
+  int32_t sx, sy, sz;      /* Slope::morton_xy (as signed indices) and Slope::morton_z    */
+  float mean[3];           /* Slope::mean                                                 */
+  float normal[3];         /* Slope::normal                                               */
+  float rough;             /* Slope::rough                                                */
+  uint32_t flags;          /* same bits as gndt_voxel::flags                              */
+  uint32_t voxel;          /* index of the owning record in the voxel table               */
+} gndt_slope;
+
+/* One occupied x-y column = one Cell (include/map2D.h:181-187, created at :598-599). */
+typedef struct gndt_column {
+  int32_t sx, sy;          /* Cell::morton as signed indices                              */
+  uint32_t first_index;    /* min first_index over its voxels = position in morton_list   */
+  uint32_t voxel_begin;    /* first record of the column in the voxel table               */
+  uint32_t voxel_count;    /* records in the column                                       */
+  uint32_t slope_count;    /* Cell::map_slope.size()                                      */
+} gndt_column;
+
+typedef struct gndt_counts_t {
+  uint64_t n_input;        /* points handed to the last build/update                      */
+  uint64_t n_binned;       /* points that landed in a voxel of this tile                  */
+  uint64_t n_dropped;      /* non-finite or |index| > GNDT_MAX_INDEX (undefined in the
+                              reference, Stopwatch.h:102-110) — counted, never binned     */
+  uint64_t n_outside_tile; /* points of other GPUs' x strips                              */
+  uint64_t n_columns;      /* morton_list.size()  (src/receiver.cpp:158)                  */
+  uint64_t n_voxels;       /* OcNode count                                                */
+  uint64_t n_fitted;       /* voxels with count >= min_points                             */
+  uint64_t n_slopes;       /* slope_num (map2D.h:1226)                                    */
+} gndt_counts_t;
+
+/* device-timed stages of the last build, milliseconds (cudaEvent on the build stream) */
+enum {
+  GNDT_STAGE_KEY = 0,      /* bounds + first digit histogram (transMortonXYZ arithmetic)  */
+  GNDT_STAGE_SORT = 1,     /* radix partition by (cx,cy,cz) (uniformDivision's binning)   */
+  GNDT_STAGE_REDUCE = 2,   /* per-voxel moments + eigen (create2DMap fit)                 */
+  GNDT_STAGE_LABEL = 3,    /* isSlope / countUp labels + column/slope tables              */
+  GNDT_STAGE_EDGES = 4,    /* neighbour reachability bits (countReachable)                */
+  GNDT_STAGE_TOTAL = 5,    /* whole build on the device                                   */
+  GNDT_STAGE_H2D = 6,      /* host->device copy of the cloud when mem == GNDT_MEM_HOST    */
+  GNDT_N_STAGES = 8
+};
+
+typedef struct gndt_handle gndt_handle;
+
+/* library / ABI version string, never NULL */
+const char *gndt_version(void);
+/* last error text of this handle (or of the failed gndt_create when h == NULL) */
+const char *gndt_last_error(const gndt_handle *h);
+
+/*
+ * Create a builder bound to CUDA device `device`.
+ * Replaces: the global `daysun::TwoDmap map2D(0.5,0.1)` + setters
+ * (src/receiver.cpp:35,267-269).
+ */
+int gndt_create(const gndt_params *params, int device, gndt_handle **out);
+int gndt_destroy(gndt_handle *h);
+/* change parameters between builds (setLen/setZLen/setInterval, map2D.h:493-501) */
+int gndt_set_params(gndt_handle *h, const gndt_params *params);
+
+/*
+ * Build the map from one cloud.  `xyz` points at n records of `stride_bytes`
+ * bytes each whose first 12 bytes are little-endian float x,y,z (pcl::PointXYZ /
+ * the PointCloud2 payload: stride 16).  stride must be a multiple of 4, >= 12.
+ * Replaces: chatterCallback's setCloudFirst + uniformDivision loop + create2DMap
+ * (src/receiver.cpp:145-160; include/map2D.h:592-668).  Stream-ordered and
+ * asynchronous for device input; result queries synchronise the stream.
+ */
+int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem,
+               void *stream);
+
+/*
+ * Fuse one more scan into the resident map (origin and parameters of the
+ * initial build are kept; every point of the scan is binned).
+ * Replaces: changeCallback + change2DMap (src/receiver.cpp:179-212;
+ * include/map2D.h:672-822) — dead code in the reference (its point lists are
+ * never filled); contract here = the result equals one gndt_build over the
+ * concatenation of all clouds seen so far.
+ */
+int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem,
+                void *stream);
+
+/* counters the reference prints (receiver.cpp:144,158; map2D.h:1226) and friends */
+int gndt_counts(gndt_handle *h, gndt_counts_t *out);
+
+/* Copy result tables out.  cap = capacity of dst in records; returns GNDT_ERR_CAPACITY
+ * when too small.  dst_mem says where dst lives.  *n_out (optional) = records written. */
+int gndt_copy_voxels(gndt_handle *h, gndt_voxel *dst, size_t cap, int dst_mem, size_t *n_out);
+int gndt_copy_slopes(gndt_handle *h, gndt_slope *dst, size_t cap, int dst_mem, size_t *n_out);
+int gndt_copy_columns(gndt_handle *h, gndt_column *dst, size_t cap, int dst_mem, size_t *n_out);
+
+/* Zero-copy device view of the voxel table (valid until the next build/update/destroy);
+ * used by the multi-GPU tile gather.  Synchronises the build stream. */
+int gndt_device_voxels(gndt_handle *h, const gndt_voxel **dptr, size_t *n);
+
+/*
+ * Recompute the neighbour reachability bits (GNDT_F_REACH_*) of records
+ * [begin, begin+count) of an arbitrary device voxel table `table` of `n_table` records
+ * sorted like ours (e.g. the all-gathered tiles of several GPUs, so that strip
+ * boundaries see their halo).  Replaces countLRFB + countReachable + countAngle
+ * (include/map2D.h:197-296,477-482).
+ */
+int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin,
+                     size_t count, void *stream);
+
+/*
+ * Balanced x strips for `ntiles` GPUs: cuts[0..ntiles] in contiguous signed x index
+ * space such that strip t = [cuts[t], cuts[t+1]) holds ~n/ntiles points.  Every rank
+ * that passes the same cloud gets the same cuts (no communication needed).
+ */
+int gndt_plan_tiles(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem,
+                    int ntiles, int32_t *cuts, void *stream);
+
+int gndt_stage_ms(gndt_handle *h, float ms[GNDT_N_STAGES]);
+/* number of kernel launches issued by the last build/update on this handle */
+int gndt_launch_count(gndt_handle *h, uint64_t *n_launches);
+
+/* ---- host-side key helpers (pure C, no device) ------------------------------------- */
+
+/* TwoDmap::transMortonXYZ (include/map2D.h:950-976) for one position: signed non-zero
+ * indices.  Returns 0, or GNDT_ERR_INVALID_ARG when the position is non-finite / out of
+ * the +-GNDT_MAX_INDEX range. */
+int gndt_trans_morton_xyz(const float origin[3], float grid_len, float z_len,
+                          const float pos[3], int32_t *sx, int32_t *sy, int32_t *sz);
+/* countMorton (include/Stopwatch.h:116-147): bits of nx to odd, ny to even positions. */
+uint32_t gndt_count_morton(uint32_t nx, uint32_t ny);
+/* mortonToXY (include/Stopwatch.h:171-189) */
+void gndt_morton_to_xy(uint32_t morton, uint32_t *nx, uint32_t *ny);
+/* The reference's string key: quadrant letter + decimal Morton, e.g. "A55".
+ * buf must hold >= 16 chars.  Returns the string length. */
+int gndt_morton_string(int32_t sx, int32_t sy, char *buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNDT_H */
