@@ -76,7 +76,7 @@ VOXEL_DTYPE = np.dtype(
         ("sx", "<i4"), ("sy", "<i4"), ("sz", "<i4"),
         ("count", "<u4"), ("first_index", "<u4"),
         ("mean", "<f4", (3,)), ("scatter", "<f4", (6,)), ("evals", "<f4", (3,)),
-        ("normal", "<f4", (3,)), ("rough", "<f4"), ("flags", "<u4"), ("reserved", "<u4", (2,)),
+        ("normal", "<f4", (3,)), ("rough", "<f4"), ("flags", "<u4"), ("column", "<u4"), ("slope", "<u4"),
     ]
 )
 SLOPE_DTYPE = np.dtype(
@@ -89,10 +89,11 @@ SLOPE_DTYPE = np.dtype(
 COLUMN_DTYPE = np.dtype(
     [
         ("sx", "<i4"), ("sy", "<i4"), ("first_index", "<u4"),
-        ("voxel_begin", "<u4"), ("voxel_count", "<u4"), ("slope_count", "<u4"),
+        ("voxel_begin", "<u4"), ("voxel_count", "<u4"), ("slope_begin", "<u4"), ("slope_count", "<u4"),
+        ("reserved", "<u4"),
     ]
 )
-assert VOXEL_DTYPE.itemsize == 96 and SLOPE_DTYPE.itemsize == 48 and COLUMN_DTYPE.itemsize == 24
+assert VOXEL_DTYPE.itemsize == 96 and SLOPE_DTYPE.itemsize == 48 and COLUMN_DTYPE.itemsize == 32
 
 
 class Counts(C.Structure):

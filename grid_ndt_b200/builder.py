@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference's map-construction interface, above the C ABI.
+
+`TwoDmap` keeps the names and argument meaning of daysun::TwoDmap for this path
+(include/map2D.h:485-507: setLen/setZLen/setInterval/setCloudFirst/getGridLen/...,
+create2DMap(demand), change2DMap(), transMortonXYZ, the public containers morton_list /
+map_cell / map_xy) and of the receiver's hot loops (src/receiver.cpp:145-162).  All compute
+happens in libgndt.so on the GPU; this file only marshals buffers and builds views.
+"""
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from ._abi import COLUMN_DTYPE, SLOPE_DTYPE, VOXEL_DTYPE, Counts, Params, default_params
+from ._lib import GndtError, lib
+
+try:  # torch is only plumbing here: device memory + streams + distributed
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _check(h, rc):
+    if rc != 0:
+        msg = lib().gndt_last_error(h)
+        raise GndtError(rc, msg.decode() if msg else "")
+
+
+def morton_string(sx: int, sy: int) -> str:
+    """Quadrant letter + decimal Morton code, the reference's cell key
+    (include/map2D.h:971-972, include/Stopwatch.h:116-147)."""
+    buf = C.create_string_buffer(16)
+    lib().gndt_morton_string(int(sx), int(sy), buf)
+    return buf.value.decode()
+
+
+def morton_strings(sx: np.ndarray, sy: np.ndarray) -> np.ndarray:
+    """Vectorised morton_string for arrays of signed indices."""
+    ax, ay = np.abs(sx).astype(np.uint64), np.abs(sy).astype(np.uint64)
+    m = np.zeros(ax.shape, np.uint64)
+    for k in range(16):
+        m |= ((ax >> np.uint64(k)) & np.uint64(1)) << np.uint64(2 * k + 1)
+        m |= ((ay >> np.uint64(k)) & np.uint64(1)) << np.uint64(2 * k)
+    q = np.where(sx > 0, np.where(sy > 0, "A", "B"), np.where(sy > 0, "C", "D"))
+    return np.char.add(q, m.astype(np.int64).astype(str))
+
+
+class Slope:
+    """View of one gndt_slope record with the reference's field names (map2D.h:136-146)."""
+
+    __slots__ = ("normal", "rough", "mean", "h", "g", "f", "morton_xy", "morton_z", "up", "down", "father", "flags")
+
+    def __init__(self, rec, key):
+        self.normal = np.array(rec["normal"])
+        self.rough = float(rec["rough"])
+        self.mean = np.array(rec["mean"])
+        self.h = self.g = self.f = np.finfo(np.float32).max  # FLT_MAX (map2D.h:637)
+        self.morton_xy = key
+        self.morton_z = int(rec["sz"])
+        self.flags = int(rec["flags"])
+        self.up = False  # never assigned on the initial build (map2D.h:636)
+        self.down = bool(self.flags & _abi.F_DOWN)
+        self.father = None
+
+
+class Cell:
+    """map2D.h:181-187."""
+
+    def __init__(self, morton):
+        self._morton = morton
+        self.map_slope = {}
+
+    def getMorton(self):
+        return self._morton
+
+
+class TwoDmap:
+    """GPU-backed drop-in for daysun::TwoDmap's construction path."""
+
+    def __init__(self, res: float = 0.5, zres: float = 0.1, device: Optional[int] = None):
+        self._p = default_params(res, zres)
+        self._device = device if device is not None else (torch.cuda.current_device() if torch is not None and torch.cuda.is_available() else 0)
+        self._h = C.c_void_p()
+        rc = lib().gndt_create(C.byref(self._p), int(self._device), C.byref(self._h))
+        if rc != 0:
+            raise GndtError(rc, lib().gndt_last_error(None).decode())
+        self._cloud = None
+        self._keep = None
+        self._tables = {}
+        self._views = {}
+
+    # ---- parameter setters / getters (map2D.h:487-501) ----------------------------------
+    def setLen(self, v): self._p.grid_len = np.float32(v)
+    def setZLen(self, v): self._p.z_len = np.float32(v)
+    def setInterval(self, v): self._p.slope_interval = np.float32(v)
+    def getGridLen(self): return float(self._p.grid_len)
+    def getZLen(self): return float(self._p.z_len)
+    def getInterval(self): return float(self._p.slope_interval)
+
+    def setCloudFirst(self, p):
+        """Explicit origin (map2D.h:490-492).  chatterCallback() uses points[0] instead."""
+        self._p.origin_is_first_point = 0
+        for i in range(3):
+            self._p.origin[i] = np.float32(p[i])
+
+    def setTile(self, lo: int, hi: int):
+        """Multi-GPU x strip [lo, hi) in contiguous signed column index; lo >= hi disables."""
+        self._p.tile_lo, self._p.tile_hi = int(lo), int(hi)
+
+    @property
+    def params(self) -> Params:
+        return self._p
+
+    # ---- the hot path --------------------------------------------------------------------
+    def _marshal(self, cloud):
+        if torch is not None and isinstance(cloud, torch.Tensor):
+            if cloud.dtype != torch.float32 or cloud.dim() != 2 or cloud.shape[1] < 3 or not cloud.is_contiguous():
+                raise GndtError(-1, "cloud tensor must be contiguous float32 [n, >=3]")
+            mem = _abi.GNDT_MEM_DEVICE if cloud.is_cuda else _abi.GNDT_MEM_HOST
+            stream = torch.cuda.current_stream(cloud.device).cuda_stream if cloud.is_cuda else 0
+            return cloud.data_ptr(), cloud.shape[0], cloud.shape[1] * 4, mem, stream, cloud
+        arr = np.ascontiguousarray(cloud, dtype=np.float32)
+        if arr.ndim != 2 or arr.shape[1] < 3:
+            raise GndtError(-1, "cloud must be float32 [n, >=3]")
+        return arr.ctypes.data, arr.shape[0], arr.shape[1] * 4, _abi.GNDT_MEM_HOST, 0, arr
+
+    def uniformDivision(self, cloud):
+        """Stage the cloud to be binned: the batched form of the receiver's per-point loop
+        (src/receiver.cpp:150-154).  Binning itself runs on the GPU in create2DMap()."""
+        self._cloud = cloud
+
+    def create2DMap(self, demand: str = "slope", stream: Optional[int] = None) -> bool:
+        """Bin + fit + label the staged cloud (map2D.h:592-668).  Returns True like the
+        reference; any other demand string yields no Slopes there and is rejected here."""
+        if self._cloud is None:
+            raise GndtError(-4, "create2DMap: no cloud staged (call uniformDivision first)")
+        if demand not in ("slope", "true"):
+            raise GndtError(-1, f"unknown demand {demand!r} (the reference builds no Slopes for it)")
+        self._p.demand = _abi.GNDT_DEMAND_SLOPE if demand == "slope" else _abi.GNDT_DEMAND_TRUE
+        ptr, n, stride, mem, st, keep = self._marshal(self._cloud)
+        if stream is not None:
+            st = stream
+        L = lib()
+        _check(self._h, L.gndt_set_params(self._h, C.byref(self._p)))
+        _check(self._h, L.gndt_build(self._h, ptr, n, stride, mem, st))
+        self._keep = keep  # device input must outlive the asynchronous build
+        self._tables.clear()
+        self._views.clear()
+        return True
+
+    def chatterCallback(self, cloud, demand: str = "slope") -> bool:
+        """setCloudFirst(points[0]) + division loop from i=1 + create2DMap
+        (src/receiver.cpp:145-160)."""
+        self._p.origin_is_first_point = 1
+        self.uniformDivision(cloud)
+        return self.create2DMap(demand)
+
+    def change2DMap(self, scan) -> bool:
+        """Fuse one more scan into the resident map (map2D.h:672-822 / receiver.cpp:179-212)."""
+        ptr, n, stride, mem, st, keep = self._marshal(scan)
+        _check(self._h, lib().gndt_update(self._h, ptr, n, stride, mem, st))
+        self._keep = keep
+        self._tables.clear()
+        self._views.clear()
+        return True
+
+    # ---- results -------------------------------------------------------------------------
+    def counts(self) -> dict:
+        c = Counts()
+        _check(self._h, lib().gndt_counts(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def _table(self, name, fn, dtype, n):
+        if name not in self._tables:
+            out = np.zeros(max(n, 1), dtype)
+            got = C.c_size_t()
+            _check(self._h, fn(self._h, out.ctypes.data, n, _abi.GNDT_MEM_HOST, C.byref(got)))
+            self._tables[name] = out[: got.value]
+        return self._tables[name]
+
+    @property
+    def voxels(self) -> np.ndarray:
+        return self._table("voxels", lib().gndt_copy_voxels, VOXEL_DTYPE, self.counts()["n_voxels"])
+
+    @property
+    def slopes(self) -> np.ndarray:
+        return self._table("slopes", lib().gndt_copy_slopes, SLOPE_DTYPE, self.counts()["n_slopes"])
+
+    @property
+    def columns(self) -> np.ndarray:
+        return self._table("columns", lib().gndt_copy_columns, COLUMN_DTYPE, self.counts()["n_columns"])
+
+    def device_voxels(self):
+        """(device pointer, n) of the resident voxel table (zero copy)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(self._h, lib().gndt_device_voxels(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def label_edges(self, table_ptr: int, n_table: int, begin: int, count: int, stream: int = 0):
+        _check(self._h, lib().gndt_label_edges(self._h, table_ptr, n_table, begin, count, stream))
+
+    def plan_tiles(self, cloud, ntiles: int) -> np.ndarray:
+        ptr, n, stride, mem, st, keep = self._marshal(cloud)
+        cuts = (C.c_int32 * (ntiles + 1))()
+        L = lib()
+        _check(self._h, L.gndt_set_params(self._h, C.byref(self._p)))
+        _check(self._h, L.gndt_plan_tiles(self._h, ptr, n, stride, mem, ntiles, cuts, st))
+        return np.array(cuts[:], np.int32)
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * _abi.N_STAGES)()
+        _check(self._h, lib().gndt_stage_ms(self._h, ms))
+        return {k: float(ms[i]) for i, k in enumerate(_abi.STAGE_NAMES) if k != "reserved"}
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _check(self._h, lib().gndt_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def transMortonXYZ(self, position, origin=None):
+        """(morton_xy string, morton_z) of a position (map2D.h:950-976)."""
+        o = origin if origin is not None else [self._p.origin[i] for i in range(3)]
+        oo = (C.c_float * 3)(*[np.float32(v) for v in o])
+        pp = (C.c_float * 3)(*[np.float32(v) for v in position])
+        sx, sy, sz = C.c_int32(), C.c_int32(), C.c_int32()
+        rc = lib().gndt_trans_morton_xyz(oo, self._p.grid_len, self._p.z_len, pp, C.byref(sx), C.byref(sy), C.byref(sz))
+        if rc != 0:
+            raise GndtError(rc, "position outside the supported index range")
+        return morton_string(sx.value, sy.value), sz.value
+
+    # ---- the reference's public containers, rebuilt lazily on the host -------------------
+    @property
+    def morton_list(self):
+        """xy keys in first-seen order (receiver.cpp:70): columns sorted by first_index."""
+        if "morton_list" not in self._views:
+            cols = self.columns
+            order = np.argsort(cols["first_index"], kind="stable")
+            self._views["morton_list"] = list(morton_strings(cols["sx"][order], cols["sy"][order]))
+        return self._views["morton_list"]
+
+    @property
+    def map_cell(self):
+        """dict key -> Cell with map_slope {z: Slope}; one Cell per occupied column, even
+        with no Slope (map2D.h:598-599)."""
+        if "map_cell" not in self._views:
+            cols, sl = self.columns, self.slopes
+            keys = morton_strings(cols["sx"], cols["sy"])
+            cells = {}
+            for c, key in zip(cols, keys):
+                cell = Cell(str(key))
+                for s in sl[c["slope_begin"]: c["slope_begin"] + c["slope_count"]]:
+                    cell.map_slope[int(s["sz"])] = Slope(s, str(key))
+                cells[str(key)] = cell
+            self._views["map_cell"] = cells
+        return self._views["map_cell"]
+
+    def close(self):
+        if self._h:
+            lib().gndt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,522 @@
+// gndt_api.cu — C ABI of libgndt.so (include/gndt.h): handle, device workspace, the fixed
+// launch sequence of one map build, result accessors and the host-side key helpers.
+//
+// One build = bounds -> plan -> up to 6 partition passes -> reduce -> fixup -> label ->
+// column_finish -> edges, all stream-ordered with no host round trip; counts are read
+// back only when the caller asks for them.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "gndt_device.cuh"
+#include "gndt_label.cuh"
+#include "gndt_reduce.cuh"
+#include "gndt_sort.cuh"
+
+using namespace gndt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Buffer {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+enum EvId { EV_H2D0, EV_START, EV_KEY, EV_SORT, EV_REDUCE, EV_LABEL, EV_EDGES, EV_COUNT };
+
+}  // namespace
+
+struct gndt_handle {
+  int device = 0;
+  gndt_params params;
+  std::string err;
+  // workspace
+  Buffer in_stage, buf_a, buf_b, table, slopes, columns, zero;
+  size_t cap_points = 0, cap_voxels = 0;
+  // carved out of `zero`
+  Ctl *ctl = nullptr;
+  Ctl *ctl2 = nullptr;  // scratch control block for gndt_label_edges on foreign tables
+  u32 *hist = nullptr;
+  u32 *row_start = nullptr, *row_end = nullptr;
+  u32 *lb = nullptr;
+  u32 *tile_state = nullptr;
+  TileCarry *carry = nullptr;
+  u64 *blk_state = nullptr;
+  size_t zero_bytes_used = 0;
+  size_t sort_tiles = 0, red_tiles = 0, label_blocks = 0;
+  // foreign-table scratch
+  Buffer f_slopes, f_columns, f_zero;
+  // state
+  bool built = false;
+  bool counts_valid = false;
+  Ctl host_ctl;
+  size_t n_input = 0;
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t ev[EV_COUNT] = {};
+  bool timed_h2d = false;
+  uint64_t launches = 0;
+  int sm_count = 148;
+};
+
+namespace {
+
+#define GNDT_CUDA(h, call)                                                                   \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+      return GNDT_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+int ensure(gndt_handle *h, Buffer &b, size_t bytes) {
+  if (b.bytes >= bytes) return GNDT_OK;
+  if (b.p) GNDT_CUDA(h, cudaFree(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  GNDT_CUDA(h, cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return GNDT_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+DevParams to_dev(const gndt_params &p, size_t cap_voxels) {
+  DevParams d;
+  d.grid_len = p.grid_len; d.z_len = p.z_len; d.slope_interval = p.slope_interval;
+  d.demand = p.demand; d.min_points = p.min_points;
+  d.rough_max = p.rough_max; d.angle_max_deg = p.angle_max_deg; d.reach_height = p.reach_height;
+  d.origin_first = p.origin_is_first_point;
+  d.origin[0] = p.origin[0]; d.origin[1] = p.origin[1]; d.origin[2] = p.origin[2];
+  d.normalize_cov = p.normalize_cov;
+  d.tile_lo = p.tile_lo; d.tile_hi = p.tile_hi;
+  d.max_voxels = (u32)cap_voxels;
+  return d;
+}
+
+int validate_params(const gndt_params *p) {
+  if (!p) return GNDT_ERR_INVALID_ARG;
+  if (!(p->grid_len > 0.f) || !(p->z_len > 0.f) || !std::isfinite(p->grid_len) || !std::isfinite(p->z_len))
+    return GNDT_ERR_INVALID_ARG;
+  if (p->demand != GNDT_DEMAND_SLOPE && p->demand != GNDT_DEMAND_TRUE) return GNDT_ERR_INVALID_ARG;
+  if (p->min_points < 1) return GNDT_ERR_INVALID_ARG;
+  return GNDT_OK;
+}
+
+// Size the workspace for n points and carve the zero-initialised region.
+int reserve(gndt_handle *h, size_t n, bool host_input, size_t stride_bytes) {
+  const size_t cap_vox = h->params.max_voxels ? (size_t)h->params.max_voxels : n;
+  int rc;
+  if (host_input && (rc = ensure(h, h->in_stage, n * stride_bytes)) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->buf_a, n * sizeof(float4))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->buf_b, n * sizeof(float4))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->table, cap_vox * sizeof(gndt_voxel))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->slopes, cap_vox * sizeof(gndt_slope))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->columns, cap_vox * sizeof(gndt_column))) != GNDT_OK) return rc;
+  h->cap_points = n;
+  h->cap_voxels = cap_vox;
+  h->sort_tiles = (n + kSortTile - 1) / kSortTile;
+  h->red_tiles = (n + kRedTile - 1) / kRedTile;
+  h->label_blocks = (cap_vox + kLabelThreads - 1) / kLabelThreads;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_ctl = carve(sizeof(Ctl));
+  const size_t o_ctl2 = carve(sizeof(Ctl));
+  const size_t o_hist = carve((kMaxPasses + 1) * kRadixBins * sizeof(u32));
+  const size_t o_rs = carve(65536 * sizeof(u32));
+  const size_t o_re = carve(65536 * sizeof(u32));
+  const size_t o_lb = carve((size_t)kMaxPasses * h->sort_tiles * kRadixBins * sizeof(u32));
+  const size_t o_ts = carve(h->red_tiles * sizeof(u32));
+  const size_t o_ca = carve(h->red_tiles * sizeof(TileCarry));
+  const size_t o_bs = carve(h->label_blocks * sizeof(u64));
+  if ((rc = ensure(h, h->zero, off)) != GNDT_OK) return rc;
+  char *z = static_cast<char *>(h->zero.p);
+  h->ctl = reinterpret_cast<Ctl *>(z + o_ctl);
+  h->ctl2 = reinterpret_cast<Ctl *>(z + o_ctl2);
+  h->hist = reinterpret_cast<u32 *>(z + o_hist);
+  h->row_start = reinterpret_cast<u32 *>(z + o_rs);
+  h->row_end = reinterpret_cast<u32 *>(z + o_re);
+  h->lb = reinterpret_cast<u32 *>(z + o_lb);
+  h->tile_state = reinterpret_cast<u32 *>(z + o_ts);
+  h->carry = reinterpret_cast<TileCarry *>(z + o_ca);
+  h->blk_state = reinterpret_cast<u64 *>(z + o_bs);
+  h->zero_bytes_used = off;
+  return GNDT_OK;
+}
+
+int grid_for(const gndt_handle *h, size_t work_items, int per_block, int max_waves) {
+  size_t blocks = (work_items + per_block - 1) / per_block;
+  size_t cap = (size_t)h->sm_count * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int sync_counts(gndt_handle *h) {
+  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
+  if (h->counts_valid) return GNDT_OK;
+  GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  GNDT_CUDA(h, cudaMemcpy(&h->host_ctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+  if (h->host_ctl.err & kErrWatchdog) { h->err = "device watchdog tripped (look-back never resolved)"; return GNDT_ERR_INTERNAL; }
+  if (h->host_ctl.err & kErrCapacity) { h->err = "voxel table capacity (max_voxels) exceeded"; return GNDT_ERR_CAPACITY; }
+  h->counts_valid = true;
+  return GNDT_OK;
+}
+
+// label -> column_finish -> edges on (table, n) with the handle's own control block.
+int launch_label_and_edges(gndt_handle *h, cudaStream_t st, const DevParams &dp) {
+  const int g_lab = grid_for(h, h->cap_voxels, kLabelThreads, 8);
+  label_kernel<<<g_lab, kLabelThreads, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, 0u, (gndt_slope *)h->slopes.p,
+                                                (gndt_column *)h->columns.p, h->blk_state, &h->ctl->ticket[7], 1, dp);
+  column_finish_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, 0u, (gndt_column *)h->columns.p,
+                                              h->row_start, h->row_end, 0, 0);
+  h->launches += 2;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_LABEL], st));
+  edges_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
+                                      (const gndt_column *)h->columns.p, h->row_start, h->row_end, 0, 0, 0, 0u,
+                                      0xFFFFFFFFu, dp);
+  h->launches += 1;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_EDGES], st));
+  return GNDT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gndt_version(void) { return "gndt 0.1 (abi 1, sm_100a)"; }
+
+const char *gndt_last_error(const gndt_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void gndt_default_params(gndt_params *p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->grid_len = 0.5f; p->z_len = 0.1f; p->slope_interval = 0.08f;
+  p->demand = GNDT_DEMAND_SLOPE; p->min_points = 3;
+  p->rough_max = 100.f; p->angle_max_deg = 30.f; p->reach_height = 0.15f;
+  p->origin_is_first_point = 1;
+}
+
+int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
+  if (!out) return GNDT_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (validate_params(params) != GNDT_OK) { g_create_error = "invalid gndt_params"; return GNDT_ERR_INVALID_ARG; }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || device < 0 || device >= n_dev) {
+    g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+    return GNDT_ERR_CUDA;
+  }
+  gndt_handle *h = new gndt_handle();
+  h->device = device;
+  h->params = *params;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  for (int i = 0; i < EV_COUNT; ++i)
+    if ((e = cudaEventCreate(&h->ev[i])) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
+  e = cudaFuncSetAttribute(sort_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
+  if (e != cudaSuccess) { g_create_error = std::string("kernel image for sm_100a not loadable on this device: ") + cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
+  *out = h;
+  return GNDT_OK;
+}
+
+int gndt_destroy(gndt_handle *h) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->table, &h->slopes, &h->columns, &h->zero,
+                    &h->f_slopes, &h->f_columns, &h->f_zero};
+  for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
+  for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return GNDT_OK;
+}
+
+int gndt_set_params(gndt_handle *h, const gndt_params *params) {
+  if (!h || validate_params(params) != GNDT_OK) return GNDT_ERR_INVALID_ARG;
+  h->params = *params;
+  return GNDT_OK;
+}
+
+int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  if (!xyz || n == 0 || stride_bytes < 12 || (stride_bytes & 3) || (mem != GNDT_MEM_HOST && mem != GNDT_MEM_DEVICE)) {
+    h->err = "gndt_build: bad argument (xyz NULL, n == 0, stride not a multiple of 4 >= 12, or bad mem)";
+    return GNDT_ERR_INVALID_ARG;
+  }
+  if (n > GNDT_MAX_POINTS) { h->err = "gndt_build: n exceeds GNDT_MAX_POINTS"; return GNDT_ERR_CAPACITY; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  h->built = false;
+  h->counts_valid = false;
+  h->launches = 0;
+  int rc = reserve(h, n, mem == GNDT_MEM_HOST, stride_bytes);
+  if (rc != GNDT_OK) return rc;
+
+  const float *d_in = static_cast<const float *>(xyz);
+  h->timed_h2d = false;
+  if (mem == GNDT_MEM_HOST) {
+    GNDT_CUDA(h, cudaEventRecord(h->ev[EV_H2D0], st));
+    GNDT_CUDA(h, cudaMemcpyAsync(h->in_stage.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, st));
+    d_in = static_cast<const float *>(h->in_stage.p);
+    h->timed_h2d = true;
+  }
+  const size_t stride_f = stride_bytes / 4;
+  const size_t start = h->params.origin_is_first_point ? 1 : 0;
+  const DevParams dp = to_dev(h->params, h->cap_voxels);
+
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
+  GNDT_CUDA(h, cudaMemsetAsync(h->zero.p, 0, h->zero_bytes_used, st));
+
+  // K1: bounds + first-digit histogram, then the key layout
+  bounds_kernel<<<grid_for(h, n, 256 * 8, 8), 256, 0, st>>>(h->ctl, h->hist, d_in, stride_f, n, start, dp);
+  plan_kernel<<<1, 32, 0, st>>>(h->ctl);
+  h->launches += 2;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_KEY], st));
+
+  // K2: partition passes (pass p writes buffer A when p is even, B when odd)
+  const int tiles = (int)h->sort_tiles;
+  float4 *A = static_cast<float4 *>(h->buf_a.p), *B = static_cast<float4 *>(h->buf_b.p);
+  sort_pass_kernel<true><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
+      h->ctl, 0, d_in, stride_f, n, start, nullptr, A, h->lb, h->hist, h->hist + kRadixBins, dp);
+  for (int p = 1; p < kMaxPasses; ++p) {
+    const float4 *src = (p & 1) ? A : B;
+    float4 *dst = (p & 1) ? B : A;
+    sort_pass_kernel<false><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
+        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins,
+        h->hist + (size_t)p * kRadixBins, h->hist + (size_t)(p + 1) * kRadixBins, dp);
+  }
+  h->launches += kMaxPasses;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));
+
+  // K3: per-voxel fit
+  reduce_kernel<<<(int)h->red_tiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, (gndt_voxel *)h->table.p,
+                                                                         h->carry, h->tile_state, dp);
+  fixup_kernel<<<grid_for(h, h->red_tiles, 128, 4), 128, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, h->carry, dp);
+  h->launches += 2;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_REDUCE], st));
+
+  // K4/K5
+  rc = launch_label_and_edges(h, st, dp);
+  if (rc != GNDT_OK) return rc;
+  GNDT_CUDA(h, cudaGetLastError());
+  h->built = true;
+  h->n_input = n;
+  h->last_stream = st;
+  return GNDT_OK;
+}
+
+int gndt_update(gndt_handle *h, const void *, size_t, size_t, int, void *) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  h->err = "gndt_update: streaming merge is not available in this build";
+  return GNDT_ERR_STATE;
+}
+
+int gndt_counts(gndt_handle *h, gndt_counts_t *out) {
+  if (!h || !out) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  const Ctl &c = h->host_ctl;
+  out->n_input = h->n_input;
+  out->n_binned = c.n_valid;
+  out->n_dropped = c.n_dropped;
+  out->n_outside_tile = c.n_outside;
+  out->n_columns = c.n_columns;
+  out->n_voxels = c.n_voxels;
+  out->n_fitted = c.n_fitted;
+  out->n_slopes = c.n_slopes;
+  return GNDT_OK;
+}
+
+static int copy_out(gndt_handle *h, void *dst, size_t cap, int dst_mem, size_t *n_out, const void *src, size_t n,
+                    size_t rec) {
+  if (!dst && n) return GNDT_ERR_INVALID_ARG;
+  if (n > cap) { h->err = "destination capacity too small"; return GNDT_ERR_CAPACITY; }
+  if (n) GNDT_CUDA(h, cudaMemcpy(dst, src, n * rec, dst_mem == GNDT_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
+  if (n_out) *n_out = n;
+  return GNDT_OK;
+}
+
+int gndt_copy_voxels(gndt_handle *h, gndt_voxel *dst, size_t cap, int dst_mem, size_t *n_out) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  return copy_out(h, dst, cap, dst_mem, n_out, h->table.p, h->host_ctl.n_voxels, sizeof(gndt_voxel));
+}
+int gndt_copy_slopes(gndt_handle *h, gndt_slope *dst, size_t cap, int dst_mem, size_t *n_out) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  return copy_out(h, dst, cap, dst_mem, n_out, h->slopes.p, h->host_ctl.n_slopes, sizeof(gndt_slope));
+}
+int gndt_copy_columns(gndt_handle *h, gndt_column *dst, size_t cap, int dst_mem, size_t *n_out) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  return copy_out(h, dst, cap, dst_mem, n_out, h->columns.p, h->host_ctl.n_columns, sizeof(gndt_column));
+}
+
+int gndt_device_voxels(gndt_handle *h, const gndt_voxel **dptr, size_t *n) {
+  if (!h || !dptr || !n) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  *dptr = static_cast<const gndt_voxel *>(h->table.p);
+  *n = h->host_ctl.n_voxels;
+  return GNDT_OK;
+}
+
+__global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n) {
+  if (threadIdx.x == 0 && n) {
+    ctl->cx_min = contiguous_index(table[0].sx);
+    ctl->cx_max = contiguous_index(table[n - 1].sx);
+  }
+}
+
+int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin, size_t count, void *stream) {
+  if (!h || (!table && n_table) || begin + count > n_table || n_table > 0xFFFFFFFEull) return GNDT_ERR_INVALID_ARG;
+  if (n_table == 0) return GNDT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure(h, h->f_slopes, n_table * sizeof(gndt_slope))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->f_columns, n_table * sizeof(gndt_column))) != GNDT_OK) return rc;
+  const size_t blocks = (n_table + kLabelThreads - 1) / kLabelThreads;
+  const size_t o_rs = align_up(sizeof(Ctl), 256), o_re = o_rs + 65536 * 4, o_bs = o_re + 65536 * 4;
+  const size_t zbytes = o_bs + blocks * sizeof(u64);
+  if ((rc = ensure(h, h->f_zero, zbytes)) != GNDT_OK) return rc;
+  GNDT_CUDA(h, cudaMemsetAsync(h->f_zero.p, 0, zbytes, st));
+  char *z = static_cast<char *>(h->f_zero.p);
+  Ctl *ctl = reinterpret_cast<Ctl *>(z);
+  u32 *rs = reinterpret_cast<u32 *>(z + o_rs), *re = reinterpret_cast<u32 *>(z + o_re);
+  u64 *bs = reinterpret_cast<u64 *>(z + o_bs);
+  const DevParams dp = to_dev(h->params, n_table);
+  const int g = grid_for(h, n_table, kLabelThreads, 8);
+  table_bounds_kernel<<<1, 32, 0, st>>>(ctl, table, (u32)n_table);
+  label_kernel<<<g, kLabelThreads, 0, st>>>(ctl, table, (u32)n_table, (gndt_slope *)h->f_slopes.p,
+                                            (gndt_column *)h->f_columns.p, bs, &ctl->ticket[7], 0, dp);
+  column_finish_kernel<<<g, 256, 0, st>>>(ctl, table, (u32)n_table, (gndt_column *)h->f_columns.p, rs, re, 0, 0);
+  edges_kernel<<<g, 256, 0, st>>>(ctl, table, (gndt_slope *)h->f_slopes.p, (const gndt_column *)h->f_columns.p, rs, re,
+                                  0, 0, 0, (u32)begin, (u32)(begin + count), dp);
+  h->launches += 4;
+  GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
+__global__ void cx_hist_kernel(u32 *hist, const float *in, size_t stride_f, size_t n_in, size_t start, DevParams P) {
+  float o[3];
+  if (P.origin_first) { o[0] = __ldg(in); o[1] = __ldg(in + 1); o[2] = __ldg(in + 2); }
+  else { o[0] = P.origin[0]; o[1] = P.origin[1]; o[2] = P.origin[2]; }
+  const bool vec = (stride_f == 4) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  for (size_t i = start + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = load_point(in, stride_f, i, vec);
+    int cx, cy, cz;
+    if (point_indices(p.x, p.y, p.z, o, P.grid_len, P.z_len, cx, cy, cz)) atomicAdd(&hist[cx + kIdxBias], 1u);
+  }
+}
+
+int gndt_plan_tiles(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, int ntiles, int32_t *cuts,
+                    void *stream) {
+  if (!h || !xyz || !cuts || ntiles < 1 || n == 0 || stride_bytes < 12 || (stride_bytes & 3)) return GNDT_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  int rc;
+  const float *d_in = static_cast<const float *>(xyz);
+  if (mem == GNDT_MEM_HOST) {
+    if ((rc = ensure(h, h->in_stage, n * stride_bytes)) != GNDT_OK) return rc;
+    GNDT_CUDA(h, cudaMemcpyAsync(h->in_stage.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, st));
+    d_in = static_cast<const float *>(h->in_stage.p);
+  }
+  if ((rc = ensure(h, h->f_zero, 65536 * sizeof(u32) + 1024)) != GNDT_OK) return rc;
+  GNDT_CUDA(h, cudaMemsetAsync(h->f_zero.p, 0, 65536 * sizeof(u32), st));
+  const DevParams dp = to_dev(h->params, 0);
+  cx_hist_kernel<<<grid_for(h, n, 256 * 8, 8), 256, 0, st>>>((u32 *)h->f_zero.p, d_in, stride_bytes / 4, n,
+                                                             h->params.origin_is_first_point ? 1 : 0, dp);
+  h->launches += 1;
+  u32 *hist = (u32 *)malloc(65536 * sizeof(u32));
+  cudaError_t e = cudaMemcpyAsync(hist, h->f_zero.p, 65536 * sizeof(u32), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { free(hist); h->err = cudaGetErrorString(e); return GNDT_ERR_CUDA; }
+  uint64_t total = 0;
+  for (int i = 0; i < 65536; ++i) total += hist[i];
+  cuts[0] = -kIdxBias;
+  cuts[ntiles] = kIdxBias;
+  uint64_t acc = 0;
+  int t = 1;
+  for (int i = 0; i < 65536 && t < ntiles; ++i) {
+    acc += hist[i];
+    while (t < ntiles && acc * (uint64_t)ntiles >= total * (uint64_t)t) cuts[t++] = i - kIdxBias + 1;
+  }
+  for (; t < ntiles; ++t) cuts[t] = kIdxBias;
+  free(hist);
+  return GNDT_OK;
+}
+
+int gndt_stage_ms(gndt_handle *h, float ms[GNDT_N_STAGES]) {
+  if (!h || !ms) return GNDT_ERR_INVALID_ARG;
+  if (!h->built) return GNDT_ERR_STATE;
+  GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  for (int i = 0; i < GNDT_N_STAGES; ++i) ms[i] = 0.f;
+  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_KEY], h->ev[EV_START], h->ev[EV_KEY]));
+  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_SORT], h->ev[EV_KEY], h->ev[EV_SORT]));
+  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_REDUCE], h->ev[EV_SORT], h->ev[EV_REDUCE]));
+  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_LABEL], h->ev[EV_REDUCE], h->ev[EV_LABEL]));
+  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_EDGES], h->ev[EV_LABEL], h->ev[EV_EDGES]));
+  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_TOTAL], h->ev[EV_START], h->ev[EV_EDGES]));
+  if (h->timed_h2d) GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_H2D], h->ev[EV_H2D0], h->ev[EV_START]));
+  return GNDT_OK;
+}
+
+int gndt_launch_count(gndt_handle *h, uint64_t *n_launches) {
+  if (!h || !n_launches) return GNDT_ERR_INVALID_ARG;
+  *n_launches = h->launches;
+  return GNDT_OK;
+}
+
+// ---- host key helpers ------------------------------------------------------------------
+
+static int host_axis(float p, float p0, float len, int32_t *s) {
+  volatile float d = p - p0;
+  volatile float q = std::fabs(d) / len;
+  float c = std::ceil(q);
+  if (!(c <= (float)GNDT_MAX_INDEX)) return 0;
+  int32_t n = (int32_t)c;
+  if (n == 0) n = 1;
+  *s = (p > p0) ? n : -n;
+  return 1;
+}
+
+int gndt_trans_morton_xyz(const float origin[3], float grid_len, float z_len, const float pos[3], int32_t *sx,
+                          int32_t *sy, int32_t *sz) {
+  if (!origin || !pos || !sx || !sy || !sz) return GNDT_ERR_INVALID_ARG;
+  if (!host_axis(pos[0], origin[0], grid_len, sx) || !host_axis(pos[1], origin[1], grid_len, sy) ||
+      !host_axis(pos[2], origin[2], z_len, sz))
+    return GNDT_ERR_INVALID_ARG;
+  return GNDT_OK;
+}
+
+uint32_t gndt_count_morton(uint32_t nx, uint32_t ny) {
+  uint32_t m = 0;
+  for (int k = 0; k < 16; ++k) m |= ((nx >> k) & 1u) << (2 * k + 1) | ((ny >> k) & 1u) << (2 * k);
+  return m;
+}
+
+void gndt_morton_to_xy(uint32_t morton, uint32_t *nx, uint32_t *ny) {
+  uint32_t a = 0, b = 0;
+  for (int k = 0; k < 16; ++k) { a |= ((morton >> (2 * k + 1)) & 1u) << k; b |= ((morton >> (2 * k)) & 1u) << k; }
+  if (nx) *nx = a;
+  if (ny) *ny = b;
+}
+
+int gndt_morton_string(int32_t sx, int32_t sy, char *buf) {
+  if (!buf) return 0;
+  const char q = sx > 0 ? (sy > 0 ? 'A' : 'B') : (sy > 0 ? 'C' : 'D');
+  return snprintf(buf, 16, "%c%d", q, (int)gndt_count_morton((uint32_t)abs(sx), (uint32_t)abs(sy)));
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// gndt_label.cuh — multi-level surface labels, Cell/Slope tables and local traversability.
+//
+// Replaces OcNode::isSlope (reference include/map2D.h:66-108), Slope::countUp (:147-177),
+// the Slope/Cell emission of create2DMap (:598-599,630-660) and the per-edge predicates of
+// countLRFB / countReachable / countAngle (:197-296,477-482).
+//
+// The table is sorted by (cx,cy,cz), so a voxel's vertical neighbours are the adjacent
+// records (the contiguous index has no gap at the -1/+1 crossing, map2D.h:69-75) and its
+// left/right neighbour cells are the adjacent columns; forward/back cells are found by a
+// binary search inside the neighbouring x row.
+#pragma once
+#include "gndt_device.cuh"
+
+namespace gndt {
+
+constexpr int kLabelThreads = 256;
+
+struct VoxHeader {
+  int sx, sy, sz;
+  u32 count, first;
+  float mx, my, mz;
+};
+
+__device__ __forceinline__ VoxHeader load_header(const gndt_voxel *t, size_t v) {
+  const int4 a = *reinterpret_cast<const int4 *>(t + v);
+  const int4 b = *(reinterpret_cast<const int4 *>(t + v) + 1);
+  VoxHeader h;
+  h.sx = a.x; h.sy = a.y; h.sz = a.z; h.count = (u32)a.w;
+  h.first = (u32)b.x; h.mx = __int_as_float(b.y); h.my = __int_as_float(b.z); h.mz = __int_as_float(b.w);
+  return h;
+}
+__device__ __forceinline__ int contiguous_index(int s) { return s > 0 ? s - 1 : s; }
+
+// K4: one thread per voxel.  `relabel` = false only rebuilds the column/slope tables from
+// flags already present (used on all-gathered multi-GPU tables).
+//
+// isSlope restated in closed form: processing order inside a column is
+// ascending first_index; a neighbour u contributes its centroid z only if it was fitted
+// BEFORE v (count >= min_points and first(u) < first(v)), else the constructor's 0.
+//   up(v)   = exists u at cz+1: |seen_z(u|v) - mean_z(v)| > slope_interval   (binary32)
+//   down(v) = same at cz-1;   is_slope = fitted && !up          (demand "slope")
+// demand "true": every fitted voxel is a Slope, down = false, up = countUp on FINAL
+// centroids (no order dependence).
+__global__ void __launch_bounds__(kLabelThreads)
+label_kernel(Ctl *ctl, gndt_voxel *table, u32 n_table_fixed, gndt_slope *slopes, gndt_column *columns,
+             u64 *blk_state, u32 *counters, int relabel, DevParams P) {
+  __shared__ u32 warp_sums[8];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_prefix;
+  const int tid = threadIdx.x;
+  const u32 V = n_table_fixed ? n_table_fixed : ctl->n_voxels;
+  const u32 n_blocks = (V + kLabelThreads - 1) / kLabelThreads;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(&counters[0], 1u);
+    __syncthreads();
+    const u32 blk = s_tile;
+    if (blk >= n_blocks) return;
+    const size_t v = (size_t)blk * kLabelThreads + tid;
+    const bool live = v < V;
+    VoxHeader h = {};
+    u32 flags = 0;
+    bool head = false;
+    if (live) {
+      h = load_header(table, v);
+      const u32 old_flags = table[v].flags;
+      VoxHeader lo = {}, hi = {};
+      bool has_lo = false, has_hi = false;
+      if (v > 0) { lo = load_header(table, v - 1); has_lo = (lo.sx == h.sx && lo.sy == h.sy); }
+      if (v + 1 < V) { hi = load_header(table, v + 1); has_hi = (hi.sx == h.sx && hi.sy == h.sy); }
+      head = !has_lo;
+      if (relabel) {
+        const bool fitted = (int)h.count >= P.min_points;
+        if (fitted) {
+          flags = GNDT_F_FITTED;
+          const int cz = contiguous_index(h.sz);
+          bool up = false, down = false;
+          const bool ordered = (P.demand == GNDT_DEMAND_SLOPE);
+          if (has_hi && contiguous_index(hi.sz) == cz + 1) {
+            const bool seen = (int)hi.count >= P.min_points && (!ordered || hi.first < h.first);
+            up = fabsf(__fsub_rn(seen ? hi.mz : 0.f, h.mz)) > P.slope_interval;
+          }
+          if (ordered && has_lo && contiguous_index(lo.sz) == cz - 1) {
+            const bool seen = (int)lo.count >= P.min_points && lo.first < h.first;
+            down = fabsf(__fsub_rn(seen ? lo.mz : 0.f, h.mz)) > P.slope_interval;
+          }
+          if (up) flags |= GNDT_F_UP;
+          if (down) flags |= GNDT_F_DOWN;
+          if (P.demand == GNDT_DEMAND_TRUE || !up) flags |= GNDT_F_SLOPE;
+        }
+      } else {
+        flags = old_flags & ~(u32)GNDT_F_COLUMN_HEAD;
+      }
+      if (head) flags |= GNDT_F_COLUMN_HEAD;
+    }
+    const bool slope = (flags & GNDT_F_SLOPE) != 0;
+    u32 total = 0;
+    const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
+    const u32 exc = block_exclusive_scan_256(packed, warp_sums, &total);
+    if (tid == 0) {
+      const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
+      s_prefix = lookback_u64(blk_state + blk, (int)blk, mine, &ctl->err);
+      if (blk == n_blocks - 1) {
+        const u64 incl = s_prefix + mine;
+        ctl->n_columns = (u32)(incl >> 31);
+        ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
+      }
+    }
+    const u32 fitted_cnt = __syncthreads_count(live && (flags & GNDT_F_FITTED));
+    if (tid == 0 && fitted_cnt) atomicAdd(&ctl->n_fitted, fitted_cnt);
+    if (!live) continue;
+    const u32 cols_before = (u32)(s_prefix >> 31) + (exc >> 16);
+    const u32 slopes_before = (u32)(s_prefix & 0x7FFFFFFFu) + (exc & 0xFFFFu);
+    const u32 col_idx = cols_before + (head ? 1u : 0u) - 1u;
+    gndt_voxel *rec = table + v;
+    rec->flags = flags;
+    rec->column = col_idx;
+    rec->slope = slope ? slopes_before : 0xFFFFFFFFu;
+    if (slope) {
+      gndt_slope s;
+      s.sx = h.sx; s.sy = h.sy; s.sz = h.sz;
+      s.mean[0] = h.mx; s.mean[1] = h.my; s.mean[2] = h.mz;
+      s.normal[0] = rec->normal[0]; s.normal[1] = rec->normal[1]; s.normal[2] = rec->normal[2];
+      s.rough = rec->rough;
+      s.flags = flags;
+      s.voxel = (u32)v;
+      float4 *d = reinterpret_cast<float4 *>(slopes + slopes_before);
+      const float4 *q = reinterpret_cast<const float4 *>(&s);
+      d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+    }
+    if (head) {
+      gndt_column c;
+      c.sx = h.sx; c.sy = h.sy; c.first_index = h.first; c.voxel_begin = (u32)v; c.voxel_count = 0;
+      c.slope_begin = slopes_before; c.slope_count = 0; c.reserved = 0;
+      float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
+      const float4 *q = reinterpret_cast<const float4 *>(&c);
+      d[0] = q[0]; d[1] = q[1];
+    }
+  }
+}
+
+// K4b: one thread per column: extents, first-seen index (position in the reference's
+// morton_list, src/receiver.cpp:70) and the x-row directory used by the edge search.
+__global__ void column_finish_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_table_fixed,
+                                     gndt_column *columns, u32 *row_start, u32 *row_end, int cx_base_fixed,
+                                     int use_fixed_base) {
+  const u32 V = n_table_fixed ? n_table_fixed : ctl->n_voxels;
+  const u32 C = ctl->n_columns, S = ctl->n_slopes;
+  const int cx_base = use_fixed_base ? cx_base_fixed : ctl->cx_min;
+  for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    gndt_column col = columns[c];
+    const u32 v_end = (c + 1 < C) ? columns[c + 1].voxel_begin : V;
+    const u32 s_end = (c + 1 < C) ? columns[c + 1].slope_begin : S;
+    u32 first = 0xFFFFFFFFu;
+    for (u32 v = col.voxel_begin; v < v_end; ++v) first = min(first, table[v].first_index);
+    columns[c].first_index = first;
+    columns[c].voxel_count = v_end - col.voxel_begin;
+    columns[c].slope_count = s_end - col.slope_begin;
+    const int cx = contiguous_index(col.sx);
+    const int row = cx - cx_base;
+    if (c == 0 || contiguous_index(columns[c - 1].sx) != cx) row_start[row] = c;
+    if (c + 1 == C || contiguous_index(columns[c + 1].sx) != cx) row_end[row] = c + 1;
+  }
+}
+
+// TwoDmap::countAngle (map2D.h:477-482) in the reference's own mixed precision: binary32
+// dot product, binary64 norms (pow(float,int) -> double), quotient stored to float,
+// acos(float), degrees via *180 (float) then /M_PI (double) stored to float, folded to
+// <= 90.  res > 1 gives NaN, which fails the <= test exactly like the reference.
+__device__ __forceinline__ float count_angle(const float a[3], const float b[3]) {
+  float dot = __fmul_rn(a[0], b[0]);
+  dot = __fadd_rn(dot, __fmul_rn(a[1], b[1]));
+  dot = __fadd_rn(dot, __fmul_rn(a[2], b[2]));
+  const double l1 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)a[0], (double)a[0]), __dmul_rn((double)a[1], (double)a[1])),
+                                   __dmul_rn((double)a[2], (double)a[2])));
+  const double l2 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)b[0], (double)b[0]), __dmul_rn((double)b[1], (double)b[1])),
+                                   __dmul_rn((double)b[2], (double)b[2])));
+  const float res = (float)((double)dot / __dmul_rn(l1, l2));
+  const float deg = __fmul_rn(acosf(res), 180.f);
+  float an = (float)((double)deg / 3.14159265358979323846);
+  if (an > 90.f) an = __fsub_rn(180.f, an);
+  return an;
+}
+
+// Does neighbour cell `c` hold a Slope reachable from (normal n, mean z)?  countReachable's
+// four tests (map2D.h:276-279 / 284-287; thresholds robot.h:38-46).
+__device__ __forceinline__ bool cell_reachable(const gndt_column &c, const gndt_slope *slopes, const float n[3],
+                                               float mz, const DevParams &P) {
+  for (u32 s = c.slope_begin; s < c.slope_begin + c.slope_count; ++s) {
+    const gndt_slope &t = slopes[s];
+    if (t.flags & GNDT_F_UP) continue;
+    if (!(t.rough <= P.rough_max)) continue;
+    const float tn[3] = {t.normal[0], t.normal[1], t.normal[2]};
+    if (!(count_angle(tn, n) <= P.angle_max_deg)) continue;
+    if (!(fabsf(__fsub_rn(t.mean[2], mz)) <= P.reach_height)) continue;
+    return true;
+  }
+  return false;
+}
+
+// K5: one thread per Slope in [begin, begin+count): left/right = adjacent columns of the
+// same x row, forward/back = binary search for the same cy in the neighbouring x rows.
+// Index arithmetic is in contiguous space, which is countLRFB's quadrant crossing
+// (x==1 / y==1 cases, map2D.h:219-253) without the special cases.
+__global__ void __launch_bounds__(256)
+edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column *columns,
+             const u32 *row_start, const u32 *row_end, int cx_base_fixed, int cx_max_fixed, int use_fixed,
+             u32 vox_begin, u32 vox_end, DevParams P) {
+  const u32 S = ctl->n_slopes, C = ctl->n_columns;
+  const int cx_base = use_fixed ? cx_base_fixed : ctl->cx_min;
+  const int cx_max = use_fixed ? cx_max_fixed : ctl->cx_max;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+    gndt_slope me = slopes[i];
+    if (me.voxel < vox_begin || me.voxel >= vox_end) continue;
+    const u32 ci = table[me.voxel].column;
+    const int cx = contiguous_index(me.sx), cy = contiguous_index(me.sy);
+    const float n[3] = {me.normal[0], me.normal[1], me.normal[2]};
+    u32 bits = 0;
+    if (ci > 0) {  // left: cy-1
+      const gndt_column c = columns[ci - 1];
+      if (contiguous_index(c.sx) == cx && contiguous_index(c.sy) == cy - 1 && cell_reachable(c, slopes, n, me.mean[2], P))
+        bits |= GNDT_F_REACH_L;
+    }
+    if (ci + 1 < C) {  // right: cy+1
+      const gndt_column c = columns[ci + 1];
+      if (contiguous_index(c.sx) == cx && contiguous_index(c.sy) == cy + 1 && cell_reachable(c, slopes, n, me.mean[2], P))
+        bits |= GNDT_F_REACH_R;
+    }
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {  // forward: cx+1, back: cx-1
+      const int ncx = cx + (dir == 0 ? 1 : -1);
+      if (ncx < cx_base || ncx > cx_max) continue;
+      u32 lo = row_start[ncx - cx_base], hi = row_end[ncx - cx_base];
+      while (lo < hi) {  // first column of the row with cy' >= cy
+        const u32 mid = (lo + hi) >> 1;
+        if (contiguous_index(columns[mid].sy) < cy) lo = mid + 1; else hi = mid;
+      }
+      if (lo < row_end[ncx - cx_base]) {
+        const gndt_column c = columns[lo];
+        if (contiguous_index(c.sy) == cy && cell_reachable(c, slopes, n, me.mean[2], P))
+          bits |= (dir == 0 ? GNDT_F_REACH_F : GNDT_F_REACH_B);
+      }
+    }
+    if (bits) {
+      slopes[i].flags = me.flags | bits;
+      table[me.voxel].flags |= bits;
+    }
+  }
+}
+
+}  // namespace gndt

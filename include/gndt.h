@@ -96,7 +96,8 @@ typedef struct gndt_voxel {
   float normal[3];         /* unit eigenvector of evals[0] (sign arbitrary)               */
   float rough;             /* Slope::rough = evals[0], 0 -> 0.01 (map2D.h:131-132)        */
   uint32_t flags;          /* GNDT_F_*                                                    */
-  uint32_t reserved[2];
+  uint32_t column;         /* index of the voxel's Cell in the column table               */
+  uint32_t slope;          /* index of its Slope in the slope table, 0xFFFFFFFF if none   */
 } gndt_voxel;
 
 #define GNDT_F_FITTED 0x01u   /* count >= min_points: mean/scatter/eigen valid            */
@@ -125,7 +126,9 @@ typedef struct gndt_column {
   uint32_t first_index;    /* min first_index over its voxels = position in morton_list   */
   uint32_t voxel_begin;    /* first record of the column in the voxel table               */
   uint32_t voxel_count;    /* records in the column                                       */
+  uint32_t slope_begin;    /* first Slope of the column in the slope table                */
   uint32_t slope_count;    /* Cell::map_slope.size()                                      */
+  uint32_t reserved;
 } gndt_column;
 
 typedef struct gndt_counts_t {

@@ -549,17 +549,19 @@ int gndt_oracle_build(const float *xyz, size_t n, size_t stride_floats, const gn
     for (int k = 0; k < 3; ++k) { v->evals[k] = (float)nd->evals[k]; v->normal[k] = (float)nd->nrm[k]; }
     v->rough = nd->rough;
     v->flags = nd->flags;
-    if (nd->flags & GNDT_F_FITTED) R->n_fitted++;
-    if (nd->flags & GNDT_F_SLOPE) R->n_slopes++;
     if (i == 0 || order[i - 1]->col != nd->col) {
       v->flags |= GNDT_F_COLUMN_HEAD;
       gndt_column *c = &R->columns[nc];
       c->sx = nd->sx; c->sy = nd->sy; c->voxel_begin = (uint32_t)i;
+      c->slope_begin = (uint32_t)R->n_slopes;
       c->first_index = st.nodes[st.cols[nd->col].first_node].first;
       col_to_out[nd->col] = (uint32_t)nc++;
     }
     R->columns[nc - 1].voxel_count++;
-    if (nd->flags & GNDT_F_SLOPE) R->columns[nc - 1].slope_count++;
+    v->column = (uint32_t)(nc - 1);
+    v->slope = 0xFFFFFFFFu;
+    if (nd->flags & GNDT_F_FITTED) R->n_fitted++;
+    if (nd->flags & GNDT_F_SLOPE) { v->slope = (uint32_t)R->n_slopes++; R->columns[nc - 1].slope_count++; }
   }
   for (size_t c = 0; c < st.n_cols; ++c) R->morton_list[c] = col_to_out[c];
   R->division_s = t1 - t0;

@@ -193,7 +193,7 @@ int gndt_ref_build(const float *xyz, size_t n, size_t stride_floats, const gndt_
   R->voxels = (gndt_voxel *)calloc(recs.size() + 1, sizeof(gndt_voxel));
   R->columns = (gndt_column *)calloc(R->n_columns + 1, sizeof(gndt_column));
   R->morton_list = (uint32_t *)calloc(R->n_columns + 1, sizeof(uint32_t));
-  size_t nc = 0;
+  size_t nc = 0, ns = 0;
   for (size_t i = 0; i < recs.size(); ++i) {
     R->voxels[i] = recs[i].v;
     if (i == 0 || recs[i - 1].key != recs[i].key) {
@@ -201,11 +201,14 @@ int gndt_ref_build(const float *xyz, size_t n, size_t stride_floats, const gndt_
       gndt_column &c = R->columns[nc];
       c.sx = recs[i].v.sx; c.sy = recs[i].v.sy; c.voxel_begin = (uint32_t)i;
       c.first_index = col_rank[recs[i].key];  // rank in morton_list
+      c.slope_begin = (uint32_t)ns;
       R->morton_list[c.first_index] = (uint32_t)nc;
       nc++;
     }
     R->columns[nc - 1].voxel_count++;
-    if (recs[i].v.flags & GNDT_F_SLOPE) R->columns[nc - 1].slope_count++;
+    R->voxels[i].column = (uint32_t)(nc - 1);
+    R->voxels[i].slope = 0xFFFFFFFFu;
+    if (recs[i].v.flags & GNDT_F_SLOPE) { R->voxels[i].slope = (uint32_t)ns++; R->columns[nc - 1].slope_count++; }
   }
   *out = R;
   return GNDT_OK;
