@@ -1,7 +1,7 @@
 """ctypes / numpy mirror of include/gndt.h (record layouts, enums, params struct).
 
 Kept in one place so that the product binding (grid_ndt_b200.builder) and the test-side
-oracle wrapper (oracle/oracle.py) agree byte-for-byte with the C header.
+checker wrapper agree byte-for-byte with the C header.
 """
 import ctypes as C
 

@@ -1,0 +1,50 @@
+"""torchrun worker for the N>1 GPU test: every rank sees the whole cloud, plans the same
+balanced x strips, builds its strip, all-gathers over NCCL, relabels the halo, and the
+gathered map is compared with the oracle's untiled build (reach bits included)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from grid_ndt_b200 import _abi, synthetic
+from grid_ndt_b200._abi import default_params
+from grid_ndt_b200.tiles import TiledTwoDmap
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cloud = synthetic.cfg2(1_500_000, scale=0.4)
+    origin = [float(v) for v in cloud[0, :3]]
+    dev_cloud = torch.from_numpy(cloud).cuda()
+    tm = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local)
+    cuts = tm.plan(dev_cloud, origin=origin)
+    assert cuts[0] == -32768 and cuts[-1] == 32768 and np.all(np.diff(cuts) >= 0)
+    table, offsets = tm.build(dev_cloud, "slope", origin=origin, cuts=cuts, filter_points=True)
+    got = tm.gathered_numpy()
+    sizes = np.diff(offsets)
+    if rank == 0:
+        from oracle import oracle as O
+        p = default_params(0.2, 0.1, 0.08, origin=origin, origin_is_first_point=0)
+        o = O.oracle_build(cloud, p)
+        assert len(got) == o.counts["n_voxels"], (len(got), o.counts)
+        for f in ("sx", "sy", "sz", "count", "first_index"):
+            assert np.array_equal(got[f], o.voxels[f]), f
+        assert np.array_equal(got["flags"] & 0x0F, o.voxels["flags"] & 0x0F)
+        reach_bad = int(((got["flags"] ^ o.voxels["flags"]) & _abi.F_REACH_ALL != 0).sum())
+        assert reach_bad <= 5, f"reach bits differ on {reach_bad} voxels"
+        assert sizes.min() > 0.5 * sizes.mean(), f"strips unbalanced: {sizes}"
+        print("multi-gpu ok: strips", sizes.tolist(), "reach mismatches", reach_bad)
+    dist.barrier()
+    tm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
