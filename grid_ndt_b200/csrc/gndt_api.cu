@@ -35,7 +35,7 @@ struct gndt_handle {
   gndt_params params;
   std::string err;
   // workspace
-  Buffer in_stage, buf_a, buf_b, table, slopes, columns, zero;
+  Buffer in_stage, buf_a, buf_b, mom, table, slopes, columns, zero;
   size_t cap_points = 0, cap_voxels = 0;
   // carved out of `zero`
   Ctl *ctl = nullptr;
@@ -114,6 +114,7 @@ int reserve(gndt_handle *h, size_t n, bool host_input, size_t stride_bytes) {
   if (host_input && (rc = ensure(h, h->in_stage, n * stride_bytes)) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->buf_a, n * sizeof(float4))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->buf_b, n * sizeof(float4))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->mom, cap_vox * sizeof(VoxMoments))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->table, cap_vox * sizeof(gndt_voxel))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->slopes, cap_vox * sizeof(gndt_slope))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->columns, cap_vox * sizeof(gndt_column))) != GNDT_OK) return rc;
@@ -170,8 +171,9 @@ int sync_counts(gndt_handle *h) {
 // label -> column_finish -> edges on (table, n) with the handle's own control block.
 int launch_label_and_edges(gndt_handle *h, cudaStream_t st, const DevParams &dp) {
   const int g_lab = grid_for(h, h->cap_voxels, kLabelThreads, 8);
-  label_kernel<<<g_lab, kLabelThreads, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, 0u, (gndt_slope *)h->slopes.p,
-                                                (gndt_column *)h->columns.p, h->blk_state, &h->ctl->ticket[7], 1, dp);
+  finalize_label_kernel<<<g_lab, kLabelThreads, 0, st>>>(h->ctl, (const VoxMoments *)h->mom.p, (gndt_voxel *)h->table.p,
+                                                         (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p,
+                                                         h->blk_state, &h->ctl->ticket[7], dp);
   column_finish_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, 0u, (gndt_column *)h->columns.p,
                                               h->row_start, h->row_end, 0, 0);
   h->launches += 2;
@@ -230,7 +232,7 @@ int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
 int gndt_destroy(gndt_handle *h) {
   if (!h) return GNDT_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
-  Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->table, &h->slopes, &h->columns, &h->zero,
+  Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->mom, &h->table, &h->slopes, &h->columns, &h->zero,
                     &h->f_slopes, &h->f_columns, &h->f_zero};
   for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
   for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -283,22 +285,21 @@ int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, i
   // K2: partition passes (pass p writes buffer A when p is even, B when odd)
   const int tiles = (int)h->sort_tiles;
   float4 *A = static_cast<float4 *>(h->buf_a.p), *B = static_cast<float4 *>(h->buf_b.p);
-  sort_pass_kernel<true><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
-      h->ctl, 0, d_in, stride_f, n, start, nullptr, A, h->lb, h->hist, h->hist + kRadixBins, dp);
+  sort_pass_kernel<true><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A,
+                                                                        h->lb, h->hist, dp);
   for (int p = 1; p < kMaxPasses; ++p) {
     const float4 *src = (p & 1) ? A : B;
     float4 *dst = (p & 1) ? B : A;
     sort_pass_kernel<false><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
-        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins,
-        h->hist + (size_t)p * kRadixBins, h->hist + (size_t)(p + 1) * kRadixBins, dp);
+        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins, h->hist, dp);
   }
   h->launches += kMaxPasses;
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));
 
   // K3: per-voxel fit
-  reduce_kernel<<<(int)h->red_tiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, (gndt_voxel *)h->table.p,
+  reduce_kernel<<<(int)h->red_tiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, (VoxMoments *)h->mom.p,
                                                                          h->carry, h->tile_state, dp);
-  fixup_kernel<<<grid_for(h, h->red_tiles, 128, 4), 128, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, h->carry, dp);
+  fixup_kernel<<<grid_for(h, h->red_tiles * 32, 128, 16), 128, 0, st>>>(h->ctl, (VoxMoments *)h->mom.p, h->carry);
   h->launches += 2;
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_REDUCE], st));
 

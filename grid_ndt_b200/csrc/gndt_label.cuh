@@ -10,6 +10,7 @@
 // binary search inside the neighbouring x row.
 #pragma once
 #include "gndt_device.cuh"
+#include "gndt_reduce.cuh"
 
 namespace gndt {
 
@@ -135,6 +136,141 @@ label_kernel(Ctl *ctl, gndt_voxel *table, u32 n_table_fixed, gndt_slope *slopes,
       float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
       const float4 *q = reinterpret_cast<const float4 *>(&c);
       d[0] = q[0]; d[1] = q[1];
+    }
+  }
+}
+
+// K4 (main path): one thread per voxel, straight from the raw binary64 moments:
+//   * finish the voxel — binary32 mean / scatter, closed-form eigen, rough, normal
+//     (create2DMap's fit + countRoughNormal, map2D.h:621-623,110-133)
+//   * label it — the isSlope / countUp rules restated above, against the adjacent records
+//   * compact Slopes and Cells — CTA scan + decoupled look-back over (columns, slopes)
+// and write the 96-byte record exactly once.
+__global__ void __launch_bounds__(kLabelThreads)
+finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_slope *slopes,
+                      gndt_column *columns, u64 *blk_state, u32 *counters, DevParams P) {
+  __shared__ u32 warp_sums[8];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_prefix;
+  const int tid = threadIdx.x;
+  if (ctl->err) return;  // e.g. capacity exceeded: the moments table is incomplete
+  const u32 V = ctl->n_voxels;
+  const u32 n_blocks = (V + kLabelThreads - 1) / kLabelThreads;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(&counters[0], 1u);
+    __syncthreads();
+    const u32 blk = s_tile;
+    if (blk >= n_blocks) return;
+    const size_t v = (size_t)blk * kLabelThreads + tid;
+    const bool live = v < V;
+    float f[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) f[i] = 0.f;
+    u32 *u = reinterpret_cast<u32 *>(f);
+    u32 flags = 0;
+    bool head = false;
+    if (live) {
+      const VoxMoments me = mom[v];
+      const int cx = (int)(u32)(me.key >> 32) - kIdxBias, cy = (int)((u32)(me.key >> 16) & 0xFFFFu) - kIdxBias,
+                cz = (int)((u32)me.key & 0xFFFFu) - kIdxBias;
+      u[0] = (u32)signed_index(cx); u[1] = (u32)signed_index(cy); u[2] = (u32)signed_index(cz);
+      u[3] = me.count; u[4] = me.first;
+      const bool fitted = (int)me.count >= P.min_points;
+      const float mz = (float)me.m[2];
+      // vertical neighbours = adjacent records of the same column
+      bool has_lo = false, has_hi = false;
+      u64 lo_key = 0, hi_key = 0;
+      u32 lo_count = 0, lo_first = 0, hi_count = 0, hi_first = 0;
+      float lo_mz = 0.f, hi_mz = 0.f;
+      if (v > 0) {
+        const VoxMoments *q = mom + v - 1;
+        lo_key = q->key; lo_count = q->count; lo_first = q->first; lo_mz = (float)q->m[2];
+        has_lo = (lo_key >> 16) == (me.key >> 16);
+      }
+      if (v + 1 < V) {
+        const VoxMoments *q = mom + v + 1;
+        hi_key = q->key; hi_count = q->count; hi_first = q->first; hi_mz = (float)q->m[2];
+        has_hi = (hi_key >> 16) == (me.key >> 16);
+      }
+      head = !has_lo;
+      if (fitted) {
+        f[5] = (float)me.m[0]; f[6] = (float)me.m[1]; f[7] = mz;
+        double a[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          float s = (float)me.s[k];
+          if (P.normalize_cov) s = __fdiv_rn(s, (float)me.count);
+          f[8 + k] = s;
+          a[k] = (double)s;  // the reference's solver sees the binary32 matrix (map2D.h:111)
+        }
+        double w[3], Vv[3][3];
+        eig3_sym(a, w, Vv);
+        // OcNode::countRoughNormal's strict-< chain on the solver's diagonal (map2D.h:114-130)
+        const float e0 = (float)w[0], e1 = (float)w[1], e2 = (float)w[2];
+        int k;
+        if (e0 < e1) k = (e0 < e2) ? 0 : 2; else k = (e1 < e2) ? 1 : 2;
+        float rough = (float)w[k];
+        if (rough == 0.f) rough = 0.01f;  // map2D.h:131-132
+        double s0 = w[0], s1 = w[1], s2 = w[2], t;
+        if (s0 > s1) { t = s0; s0 = s1; s1 = t; }
+        if (s1 > s2) { t = s1; s1 = s2; s2 = t; }
+        if (s0 > s1) { t = s0; s0 = s1; s1 = t; }
+        f[14] = (float)s0; f[15] = (float)s1; f[16] = (float)s2;
+        f[17] = (float)(k == 0 ? Vv[0][0] : (k == 1 ? Vv[0][1] : Vv[0][2]));
+        f[18] = (float)(k == 0 ? Vv[1][0] : (k == 1 ? Vv[1][1] : Vv[1][2]));
+        f[19] = (float)(k == 0 ? Vv[2][0] : (k == 1 ? Vv[2][1] : Vv[2][2]));
+        f[20] = rough;
+        flags = GNDT_F_FITTED;
+        bool up = false, down = false;
+        const bool ordered = (P.demand == GNDT_DEMAND_SLOPE);
+        if (has_hi && (hi_key & 0xFFFFu) == (me.key & 0xFFFFu) + 1) {
+          const bool seen = (int)hi_count >= P.min_points && (!ordered || hi_first < me.first);
+          up = fabsf(__fsub_rn(seen ? hi_mz : 0.f, mz)) > P.slope_interval;
+        }
+        if (ordered && has_lo && (lo_key & 0xFFFFu) + 1 == (me.key & 0xFFFFu)) {
+          const bool seen = (int)lo_count >= P.min_points && lo_first < me.first;
+          down = fabsf(__fsub_rn(seen ? lo_mz : 0.f, mz)) > P.slope_interval;
+        }
+        if (up) flags |= GNDT_F_UP;
+        if (down) flags |= GNDT_F_DOWN;
+        if (P.demand == GNDT_DEMAND_TRUE || !up) flags |= GNDT_F_SLOPE;
+      }
+      if (head) flags |= GNDT_F_COLUMN_HEAD;
+    }
+    const bool slope = (flags & GNDT_F_SLOPE) != 0;
+    const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
+    u32 total = 0;
+    const u32 exc = block_exclusive_scan_256(packed, warp_sums, &total);
+    if (tid == 0) {
+      const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
+      s_prefix = lookback_u64(blk_state + blk, (int)blk, mine, &ctl->err);
+      if (blk == n_blocks - 1) {
+        const u64 incl = s_prefix + mine;
+        ctl->n_columns = (u32)(incl >> 31);
+        ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
+      }
+    }
+    const u32 fitted_cnt = __syncthreads_count(live && (flags & GNDT_F_FITTED));
+    if (tid == 0 && fitted_cnt) atomicAdd(&ctl->n_fitted, fitted_cnt);
+    if (!live) continue;
+    const u32 cols_before = (u32)(s_prefix >> 31) + (exc >> 16);
+    const u32 slopes_before = (u32)(s_prefix & 0x7FFFFFFFu) + (exc & 0xFFFFu);
+    const u32 col_idx = cols_before + (head ? 1u : 0u) - 1u;
+    u[21] = flags; u[22] = col_idx; u[23] = slope ? slopes_before : 0xFFFFFFFFu;
+    float4 *dst = reinterpret_cast<float4 *>(table + v);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    if (slope) {
+      float4 *d = reinterpret_cast<float4 *>(slopes + slopes_before);
+      d[0] = make_float4(f[0], f[1], f[2], f[5]);          // sx sy sz mean.x
+      d[1] = make_float4(f[6], f[7], f[17], f[18]);        // mean.y mean.z normal.x normal.y
+      d[2] = make_float4(f[19], f[20], __uint_as_float(flags), __uint_as_float((u32)v));
+    }
+    if (head) {
+      float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
+      d[0] = make_float4(f[0], f[1], f[4], __uint_as_float((u32)v));                // sx sy first voxel_begin
+      d[1] = make_float4(0.f, __uint_as_float(slopes_before), 0.f, 0.f);            // count slope_begin count rsvd
     }
   }
 }

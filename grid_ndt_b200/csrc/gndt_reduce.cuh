@@ -1,16 +1,17 @@
-// gndt_reduce.cuh — per-voxel NDT fit on the partitioned cloud: mean, 3x3 scatter, smallest
-// eigenpair, one 96-byte record per voxel.
+// gndt_reduce.cuh — per-voxel moments on the partitioned cloud and the closed-form eigen
+// solver used to finish a voxel.
 //
 // Replaces the fitting half of TwoDmap::create2DMap (reference include/map2D.h:606-627:
 // pcl::compute3DCentroid + pcl::computeCovarianceMatrix per OcNode with >= MINPOINTSIZE
 // points) and OcNode::countRoughNormal (map2D.h:110-133, Eigen::EigenSolver).
 //
-// Numerics: the reference sums sequentially in binary32.  Here every voxel is fitted by a
-// two-pass (mean, then centred products) binary64 accumulation over its contiguous run
-// staged in shared memory; runs that straddle tiles are merged with Chan's pairwise
-// update.  Results are rounded to binary32 once.  Two-pass + Chan keeps the reference's
-// exact zeros (all points sharing a coordinate -> that scatter row is exactly 0), which
-// its `roughness == 0 -> 0.01` rule (map2D.h:131-132) depends on.
+// Numerics: the reference sums sequentially in binary32.  Here every run (= voxel) is
+// accumulated in binary64 about its own first point (differences of two floats are exact in
+// binary64), giving (n, mean, centred scatter); runs that straddle tiles are merged with
+// Chan's pairwise update.  Results are rounded to binary32 once, in the finalize kernel.
+// Shifting by a point of the run keeps the reference's exact zeros (all points sharing a
+// coordinate -> that scatter row is exactly 0), which its `roughness == 0 -> 0.01` rule
+// (map2D.h:131-132) depends on.
 #pragma once
 #include "gndt_device.cuh"
 
@@ -19,7 +20,7 @@ namespace gndt {
 constexpr int kRedThreads = 256;
 constexpr int kRedItems = 8;
 constexpr int kRedTile = kRedThreads * kRedItems;  // 2048 points
-constexpr int kLongRun = 64;                        // runs longer than this are reduced by the whole CTA
+constexpr int kLongRun = 64;                        // longer runs are reduced by the whole CTA
 constexpr int kMaxLong = kRedTile / kLongRun;
 
 struct Moments {
@@ -28,16 +29,23 @@ struct Moments {
   double s[6];  // centred scatter xx,xy,xz,yy,yz,zz
 };
 
+// Device-resident per-voxel state (96 B, 16-byte aligned): what the finalize kernel turns
+// into a record and what the streaming merge (gndt_update) accumulates into.
+struct __align__(16) VoxMoments {
+  u64 key;      // voxel_key(cx,cy,cz)
+  u32 count;
+  u32 first;    // cloud index of the first point
+  double m[3];
+  double s[6];
+  u64 pad;
+};
+
 constexpr u32 kCarryHasLead = 1u, kCarryLeadContinues = 2u, kCarryHasTail = 4u;
 struct TileCarry {
   u32 flags;
   u32 tail_slot;
-  u32 tail_first;
-  u32 pad;
-  u64 tail_key;
-  u64 pad2;
+  u32 pad[2];
   Moments lead;  // leading run when it continues a voxel begun in an earlier tile
-  Moments tail;  // last run when its voxel continues into the next tile
 };
 
 // Chan et al. pairwise combination of two (n, mean, centred scatter) triples.
@@ -51,6 +59,17 @@ __device__ __forceinline__ void merge_moments(Moments &a, const Moments &b) {
   a.s[3] += b.s[3] + d1 * d1 * w; a.s[4] += b.s[4] + d1 * d2 * w; a.s[5] += b.s[5] + d2 * d2 * w;
   a.m[0] += d0 * f; a.m[1] += d1 * f; a.m[2] += d2 * f;
   a.n = n;
+}
+
+// Raw shifted sums (about the run's first point p0) -> (n, mean, centred scatter).
+__device__ __forceinline__ void close_moments(Moments &mo, double n, const float4 &p0, const double sd[3],
+                                              const double sq[6]) {
+  const double inv = 1.0 / n;
+  const double m0 = sd[0] * inv, m1 = sd[1] * inv, m2 = sd[2] * inv;
+  mo.n = n;
+  mo.m[0] = (double)p0.x + m0; mo.m[1] = (double)p0.y + m1; mo.m[2] = (double)p0.z + m2;
+  mo.s[0] = sq[0] - sd[0] * m0; mo.s[1] = sq[1] - sd[0] * m1; mo.s[2] = sq[2] - sd[0] * m2;
+  mo.s[3] = sq[3] - sd[1] * m1; mo.s[4] = sq[4] - sd[1] * m2; mo.s[5] = sq[5] - sd[2] * m2;
 }
 
 // One plane rotation that diagonalises the 2x2 block (app apq; apq aqq): the closed form
@@ -135,60 +154,14 @@ __device__ void eig3_sym(const double a[6], double w[3], double V[3][3]) {
   }
 }
 
-// Build and store one voxel record.
-__device__ void finalize_voxel(gndt_voxel *table, u32 slot, u64 vkey, u32 first, const Moments &mo,
-                               const DevParams &P, u32 *err) {
-  if (slot >= P.max_voxels) { atomicOr(err, kErrCapacity); return; }
-  const int cx = (int)(u32)(vkey >> 32) - kIdxBias, cy = (int)((u32)(vkey >> 16) & 0xFFFFu) - kIdxBias,
-            cz = (int)((u32)vkey & 0xFFFFu) - kIdxBias;
-  float f[24];
-#pragma unroll
-  for (int i = 0; i < 24; ++i) f[i] = 0.f;
-  u32 *u = reinterpret_cast<u32 *>(f);
-  u[0] = (u32)signed_index(cx); u[1] = (u32)signed_index(cy); u[2] = (u32)signed_index(cz);
-  const u32 count = (u32)mo.n;
-  u[3] = count; u[4] = first;
-  if ((int)count >= P.min_points) {
-    f[5] = (float)mo.m[0]; f[6] = (float)mo.m[1]; f[7] = (float)mo.m[2];
-    double a[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      float s = (float)mo.s[k];
-      if (P.normalize_cov) s = __fdiv_rn(s, (float)count);
-      f[8 + k] = s;
-      a[k] = (double)s;  // the reference's solver sees the binary32 matrix (map2D.h:111)
-    }
-    double w[3], V[3][3];
-    eig3_sym(a, w, V);
-    // OcNode::countRoughNormal's strict-< chain on the solver's diagonal (map2D.h:114-130)
-    const float e0 = (float)w[0], e1 = (float)w[1], e2 = (float)w[2];
-    int k;
-    if (e0 < e1) k = (e0 < e2) ? 0 : 2; else k = (e1 < e2) ? 1 : 2;
-    float rough = (float)w[k];
-    if (rough == 0.f) rough = 0.01f;  // map2D.h:131-132
-    double s0 = w[0], s1 = w[1], s2 = w[2], t;
-    if (s0 > s1) { t = s0; s0 = s1; s1 = t; }
-    if (s1 > s2) { t = s1; s1 = s2; s2 = t; }
-    if (s0 > s1) { t = s0; s0 = s1; s1 = t; }
-    f[14] = (float)s0; f[15] = (float)s1; f[16] = (float)s2;
-    f[17] = (float)V[0][k]; f[18] = (float)V[1][k]; f[19] = (float)V[2][k];
-    f[20] = rough;
-    u[21] = GNDT_F_FITTED;
-  }
-  float4 *dst = reinterpret_cast<float4 *>(table + slot);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-}
-
 struct RedSmem {
   float4 pts[kRedTile];
-  u64 key[kRedTile];
   unsigned short run_start[kRedTile + 2];
   unsigned short long_list[kMaxLong];
+  u64 row_last_key[kRedItems][8];  // key of the last lane of every (row, warp) for head detection
   u32 seg_cnt[kRedItems][8];
-  double red[8][6];
-  double bc[3];
-  u64 prev_key, next_key;
+  double red[8][9];
+  u64 prev_key, next_key, first_key, last_key;
   u32 n_long, tile_id, n_runs, vox_base;
 };
 
@@ -198,9 +171,49 @@ __device__ __forceinline__ u64 point_key(const float4 &p, const float o[3], cons
   return voxel_key(cx, cy, cz);
 }
 
-// K3: one CTA per tile of 2048 sorted points.
-__global__ void __launch_bounds__(kRedThreads)
-reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, gndt_voxel *table, TileCarry *carry,
+__device__ __forceinline__ void store_moments(VoxMoments *dst, u64 key, u32 first, const Moments &mo) {
+  VoxMoments v;
+  v.key = key; v.count = (u32)mo.n; v.first = first;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v.m[k] = mo.m[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v.s[k] = mo.s[k];
+  v.pad = 0;
+  const double2 *q = reinterpret_cast<const double2 *>(&v);
+  double2 *d = reinterpret_cast<double2 *>(dst);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d[i] = q[i];
+}
+
+// Warp-wide decoupled look-back over one u32 word per tile: 32 predecessors per round trip.
+// Called by one full warp; the tile's own aggregate must already be published.
+__device__ __forceinline__ u32 warp_lookback_u32(u32 *state, int tile, u32 my_count, u32 *err) {
+  const int lane = threadIdx.x & 31;
+  u32 prefix = 0;
+  for (int hi = tile - 1; hi >= 0; hi -= 32) {
+    const int j = hi - lane;
+    u32 w = kFlagIncl;  // tiles before 0 count as an inclusive zero
+    if (j >= 0) {
+      u32 spins = 0;
+      do { w = ld_relaxed(state + j); } while ((w & kFlagMask) == 0 && ++spins < kSpinLimit);
+      if ((w & kFlagMask) == 0) { atomicOr(err, kErrWatchdog); w = kFlagIncl; }
+    }
+    const u32 incl = __ballot_sync(0xffffffffu, (w & kFlagIncl) != 0);
+    const int stop = incl ? __ffs(incl) - 1 : 31;  // nearest predecessor with an inclusive prefix
+    u32 v = (lane <= stop) ? (w & kValMask) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    prefix += v;
+    if (incl) break;
+  }
+  if (lane == 0) st_relaxed(state + tile, kFlagIncl | (prefix + my_count));
+  return prefix;
+}
+
+// K3: one CTA per tile of 2048 sorted points -> raw moments of every voxel whose run starts
+// in the tile; partial runs at the tile edges go to the carry array.
+__global__ void __launch_bounds__(kRedThreads, 3)
+reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mom, TileCarry *carry,
               u32 *tile_state, DevParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RedSmem &S = *reinterpret_cast<RedSmem *>(smem_raw);
@@ -215,18 +228,31 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, gndt_voxel *ta
   const float4 *src = ((ctl->n_passes - 1) & 1) ? buf_b : buf_a;  // pass p writes A when p is even
   const float o[3] = {ctl->origin[0], ctl->origin[1], ctl->origin[2]};
 
-  // ---- stage the tile, one voxel key per point
+  // ---- stage the tile (all loads first), voxel key per point in registers
+  float4 pt[kRedItems];
 #pragma unroll
   for (int k = 0; k < kRedItems; ++k) {
     const int i = k * kRedThreads + tid;
-    if (i < cnt) {
-      const float4 p = ld_stream(src + base + i);
-      S.pts[i] = p;
-      S.key[i] = point_key(p, o, P);
-    }
+    if (i < cnt) pt[k] = ld_stream(src + base + i);
   }
-  if (tid == 0) S.prev_key = (base > 0) ? point_key(src[base - 1], o, P) : ~0ull;
-  if (tid == 32) S.next_key = (base + cnt < M) ? point_key(src[base + cnt], o, P) : ~0ull;
+  float4 edge = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0 && base > 0) edge = src[base - 1];
+  if (tid == 32 && base + cnt < M) edge = src[base + cnt];
+  u64 key[kRedItems];
+#pragma unroll
+  for (int k = 0; k < kRedItems; ++k) {
+    const int i = k * kRedThreads + tid;
+    key[k] = ~0ull;
+    if (i < cnt) {
+      S.pts[i] = pt[k];
+      key[k] = point_key(pt[k], o, P);
+    }
+    if (lane == 31) S.row_last_key[k][warp] = key[k];
+    if (i == 0) S.first_key = key[k];
+    if (i == cnt - 1) S.last_key = key[k];
+  }
+  if (tid == 0) S.prev_key = (base > 0) ? point_key(edge, o, P) : ~0ull;
+  if (tid == 32) S.next_key = (base + cnt < M) ? point_key(edge, o, P) : ~0ull;
   __syncthreads();
 
   // ---- run heads (position 0 always starts a run of this tile)
@@ -234,7 +260,9 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, gndt_voxel *ta
 #pragma unroll
   for (int k = 0; k < kRedItems; ++k) {
     const int i = k * kRedThreads + tid;
-    const bool head = (i < cnt) && (i == 0 || S.key[i] != S.key[i - 1]);
+    u64 before = __shfl_up_sync(0xffffffffu, key[k], 1);
+    if (lane == 0) before = (warp > 0) ? S.row_last_key[k][warp - 1] : (k > 0 ? S.row_last_key[k - 1][7] : ~key[k]);
+    const bool head = (i < cnt) && (i == 0 || key[k] != before);
     ball[k] = __ballot_sync(0xffffffffu, head);
     if (lane == 0) S.seg_cnt[k][warp] = __popc(ball[k]);
   }
@@ -259,17 +287,46 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, gndt_voxel *ta
     if (ball[k] & (1u << lane)) S.run_start[S.seg_cnt[k][warp] + __popc(ball[k] & ((1u << lane) - 1u))] = (unsigned short)i;
   }
   const int n_runs = (int)S.n_runs;
-  const bool first_is_head = S.prev_key != S.key[0];
-  const bool last_complete = S.next_key != S.key[cnt - 1];
+  const bool first_is_head = S.prev_key != S.first_key;
+  const bool last_complete = S.next_key != S.last_key;
+  const u32 heads = (u32)n_runs - (first_is_head ? 0u : 1u);
   if (tid == 0) {
     S.run_start[n_runs] = (unsigned short)cnt;
-    const u32 heads = (u32)n_runs - (first_is_head ? 0u : 1u);
-    const u32 vb = lookback_u32(tile_state + tile, tile, 1, heads, &ctl->err);
-    S.vox_base = vb;
-    if (base + cnt == M) ctl->n_voxels = vb + heads;
+    st_relaxed(tile_state + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | heads);  // publish early, resolve later
+  }
+  __syncthreads();
+
+  // ---- one thread per run: shifted one-pass sums from shared memory (first round kept in
+  //      registers so that the look-back below overlaps with nothing but finished work)
+  auto run_moments = [&](int j, Moments &mo) -> bool {
+    const int s = S.run_start[j], e = S.run_start[j + 1];
+    if (e - s > kLongRun) {
+      S.long_list[atomicAdd(&S.n_long, 1u)] = (unsigned short)j;
+      return false;
+    }
+    const float4 p0 = S.pts[s];
+    double sd[3] = {0, 0, 0}, sq[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = s + 1; i < e; ++i) {
+      const float4 p = S.pts[i];
+      const double dx = (double)p.x - (double)p0.x, dy = (double)p.y - (double)p0.y, dz = (double)p.z - (double)p0.z;
+      sd[0] += dx; sd[1] += dy; sd[2] += dz;
+      sq[0] += dx * dx; sq[1] += dx * dy; sq[2] += dx * dz; sq[3] += dy * dy; sq[4] += dy * dz; sq[5] += dz * dz;
+    }
+    close_moments(mo, (double)(e - s), p0, sd, sq);
+    return true;
+  };
+  Moments mo0;
+  const bool have0 = (tid < n_runs) && run_moments(tid, mo0);
+
+  if (warp == 0 && tile > 0) {
+    const u32 vb = warp_lookback_u32(tile_state, tile, heads, &ctl->err);
+    if (lane == 0) S.vox_base = vb;
+  } else if (tid == 0) {
+    S.vox_base = 0;
   }
   __syncthreads();
   const u32 vox_base = S.vox_base;
+  if (tid == 0 && base + cnt == M) ctl->n_voxels = vox_base + heads;
   TileCarry *my_carry = carry + tile;
 
   auto emit = [&](int j, const Moments &mo) {
@@ -280,40 +337,19 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, gndt_voxel *ta
     if (cont) {
       my_carry->lead = mo;
       atomicOr(&my_carry->flags, kCarryHasLead | (open_end ? kCarryLeadContinues : 0u));
-    } else if (open_end) {
-      my_carry->tail = mo;
+      return;
+    }
+    if (slot >= P.max_voxels) { atomicOr(&ctl->err, kErrCapacity); return; }
+    store_moments(mom + slot, point_key(S.pts[s], o, P), __float_as_uint(S.pts[s].w), mo);
+    if (open_end) {
       my_carry->tail_slot = slot;
-      my_carry->tail_first = __float_as_uint(S.pts[s].w);
-      my_carry->tail_key = S.key[s];
       atomicOr(&my_carry->flags, kCarryHasTail);
-    } else {
-      finalize_voxel(table, slot, S.key[s], __float_as_uint(S.pts[s].w), mo, P, &ctl->err);
     }
   };
-
-  // ---- short runs: one thread per run, two passes over shared memory
-  for (int j = tid; j < n_runs; j += kRedThreads) {
-    const int s = S.run_start[j], e = S.run_start[j + 1];
-    if (e - s > kLongRun) {
-      S.long_list[atomicAdd(&S.n_long, 1u)] = (unsigned short)j;
-      continue;
-    }
+  if (have0) emit(tid, mo0);
+  for (int j = tid + kRedThreads; j < n_runs; j += kRedThreads) {
     Moments mo;
-    double sx = 0, sy = 0, sz = 0;
-    for (int i = s; i < e; ++i) {
-      const float4 p = S.pts[i];
-      sx += (double)p.x; sy += (double)p.y; sz += (double)p.z;
-    }
-    mo.n = (double)(e - s);
-    mo.m[0] = sx / mo.n; mo.m[1] = sy / mo.n; mo.m[2] = sz / mo.n;
-    double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
-    for (int i = s; i < e; ++i) {
-      const float4 p = S.pts[i];
-      const double dx = (double)p.x - mo.m[0], dy = (double)p.y - mo.m[1], dz = (double)p.z - mo.m[2];
-      xx += dx * dx; xy += dx * dy; xz += dx * dz; yy += dy * dy; yz += dy * dz; zz += dz * dz;
-    }
-    mo.s[0] = xx; mo.s[1] = xy; mo.s[2] = xz; mo.s[3] = yy; mo.s[4] = yz; mo.s[5] = zz;
-    emit(j, mo);
+    if (run_moments(j, mo)) emit(j, mo);
   }
   __syncthreads();
 
@@ -322,60 +358,94 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, gndt_voxel *ta
   for (int l = 0; l < n_long; ++l) {
     const int j = S.long_list[l];
     const int s = S.run_start[j], e = S.run_start[j + 1];
-    double a0 = 0, a1 = 0, a2 = 0;
+    const float4 p0 = S.pts[s];
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = s + tid; i < e; i += kRedThreads) {
       const float4 p = S.pts[i];
-      a0 += (double)p.x; a1 += (double)p.y; a2 += (double)p.z;
-    }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane == 0) { S.red[warp][0] = a0; S.red[warp][1] = a1; S.red[warp][2] = a2; }
-    __syncthreads();
-    if (tid < 3) {
-      double t = 0;
-      for (int w2 = 0; w2 < 8; ++w2) t += S.red[w2][tid];
-      S.bc[tid] = t / (double)(e - s);
-    }
-    __syncthreads();
-    const double m0 = S.bc[0], m1 = S.bc[1], m2 = S.bc[2];
-    double q[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = s + tid; i < e; i += kRedThreads) {
-      const float4 p = S.pts[i];
-      const double dx = (double)p.x - m0, dy = (double)p.y - m1, dz = (double)p.z - m2;
-      q[0] += dx * dx; q[1] += dx * dy; q[2] += dx * dz; q[3] += dy * dy; q[4] += dy * dz; q[5] += dz * dz;
+      const double dx = (double)p.x - (double)p0.x, dy = (double)p.y - (double)p0.y, dz = (double)p.z - (double)p0.z;
+      acc[0] += dx; acc[1] += dy; acc[2] += dz;
+      acc[3] += dx * dx; acc[4] += dx * dy; acc[5] += dx * dz; acc[6] += dy * dy; acc[7] += dy * dz; acc[8] += dz * dz;
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) q[k] = warp_sum(q[k]);
+    for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
     if (lane == 0)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) S.red[warp][k] = q[k];
+      for (int k = 0; k < 9; ++k) S.red[warp][k] = acc[k];
     __syncthreads();
     if (tid == 0) {
-      Moments mo;
-      mo.n = (double)(e - s);
-      mo.m[0] = m0; mo.m[1] = m1; mo.m[2] = m2;
-      for (int k = 0; k < 6; ++k) {
-        double t = 0;
-        for (int w2 = 0; w2 < 8; ++w2) t += S.red[w2][k];
-        mo.s[k] = t;
+      double t[9];
+      for (int k = 0; k < 9; ++k) {
+        t[k] = 0;
+        for (int w2 = 0; w2 < 8; ++w2) t[k] += S.red[w2][k];
       }
+      Moments mo;
+      close_moments(mo, (double)(e - s), p0, t, t + 3);
       emit(j, mo);
     }
     __syncthreads();
   }
 }
 
-// K3b: voxels whose run straddles tiles: chain the partial moments in tile order.
-__global__ void fixup_kernel(Ctl *ctl, gndt_voxel *table, const TileCarry *carry, DevParams P) {
+// K3b: voxels whose run straddles tiles.  One warp per tile: a tile whose last voxel
+// continues into later tiles gathers the continuation tiles' leading partial moments 32 at
+// a time (one per lane, loaded in parallel), merges them with a fixed shuffle tree
+// (deterministic) and folds them into the voxel's stored moments.
+__global__ void __launch_bounds__(128) fixup_kernel(Ctl *ctl, VoxMoments *mom, const TileCarry *carry) {
   const size_t M = (size_t)ctl->n_valid;
   const int n_tiles = (int)((M + kRedTile - 1) / kRedTile);
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
-    if (!(carry[t].flags & kCarryHasTail)) continue;
-    Moments mo = carry[t].tail;
-    for (int u = t + 1; u < n_tiles && (carry[u].flags & kCarryHasLead); ++u) {
-      merge_moments(mo, carry[u].lead);
-      if (!(carry[u].flags & kCarryLeadContinues)) break;
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += warps_total) {
+    if (!(carry[t].flags & kCarryHasTail)) continue;  // warp-uniform
+    Moments acc;
+    acc.n = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc.m[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc.s[k] = 0.0;
+    for (int u0 = t + 1; u0 < n_tiles; u0 += 32) {
+      const int u = u0 + lane;
+      const u32 fl = (u < n_tiles) ? carry[u].flags : 0u;
+      const u32 has_lead = __ballot_sync(0xffffffffu, (fl & kCarryHasLead) != 0);
+      const u32 ends_here = __ballot_sync(0xffffffffu, (fl & kCarryHasLead) && !(fl & kCarryLeadContinues));
+      const int stop_excl = (~has_lead) ? __ffs(~has_lead) - 1 : 32;  // first tile without a lead
+      const int stop_incl = ends_here ? __ffs(ends_here) : 33;        // first tile where the voxel ends
+      const int n_inc = min(stop_excl, stop_incl);
+      Moments mine;
+      mine.n = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mine.m[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) mine.s[k] = 0.0;
+      if (lane < n_inc) mine = carry[u].lead;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {  // fixed tree: lane l absorbs lane l+o
+        Moments other;
+        other.n = __shfl_down_sync(0xffffffffu, mine.n, o);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) other.m[k] = __shfl_down_sync(0xffffffffu, mine.m[k], o);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) other.s[k] = __shfl_down_sync(0xffffffffu, mine.s[k], o);
+        if (lane + o < 32) merge_moments(mine, other);
+      }
+      if (lane == 0) merge_moments(acc, mine);
+      if (n_inc < 32) break;  // chain ended inside this chunk (warp-uniform)
     }
-    finalize_voxel(table, carry[t].tail_slot, carry[t].tail_key, carry[t].tail_first, mo, P, &ctl->err);
+    if (lane == 0) {
+      VoxMoments *v = mom + carry[t].tail_slot;
+      Moments mo;
+      mo.n = (double)v->count;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mo.m[k] = v->m[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) mo.s[k] = v->s[k];
+      merge_moments(mo, acc);
+      v->count = (u32)mo.n;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v->m[k] = mo.m[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v->s[k] = mo.s[k];
+    }
   }
 }
 

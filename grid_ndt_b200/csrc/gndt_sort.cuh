@@ -15,8 +15,17 @@
 
 namespace gndt {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 12;
+#ifndef GNDT_SORT_THREADS
+#define GNDT_SORT_THREADS 384
+#endif
+#ifndef GNDT_SORT_ITEMS
+#define GNDT_SORT_ITEMS 8
+#endif
+#ifndef GNDT_SORT_MINBLOCKS
+#define GNDT_SORT_MINBLOCKS 2
+#endif
+constexpr int kSortThreads = GNDT_SORT_THREADS;
+constexpr int kSortItems = GNDT_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 3072 points = 48 KB staged
 constexpr int kSortWarps = kSortThreads / 32;
 
@@ -26,9 +35,10 @@ struct SortSmem {
   u32 whist[kSortWarps][kRadixBins];
   u32 tile_off[kRadixBins];
   u32 gbase[kRadixBins];
-  u32 next_hist[kRadixBins];
-  u32 warp_sums[8];
+  u32 later_hist[kMaxPasses - 1][kRadixBins];  // pass 0 only: digit histograms of passes 1..5
+  u32 warp_sums[16];
   u32 tile_id;
+  u32 n_valid_tile;
 };
 
 // Load point i of a strided cloud (first 12 bytes of each record are x,y,z).
@@ -69,7 +79,11 @@ __global__ void __launch_bounds__(256) bounds_kernel(Ctl *ctl, u32 *hist0, const
     n_ok++;
     mx = max(mx, cx); my = max(my, cy); mz = max(mz, cz);
     nx = max(nx, -cx); ny = max(ny, -cy); nz = max(nz, -cz);
-    atomicAdd(&sh[first_digit(cz)], 1u);
+    {  // warp-aggregated: flat scenes put most of a warp into one z bin
+      const u32 d = first_digit(cz);
+      const u32 peers = __match_any_sync(__activemask(), d);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[d], (u32)__popc(peers));
+    }
   }
 #pragma unroll
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -136,21 +150,22 @@ __global__ void plan_kernel(Ctl *ctl) {
 
 // ---------------------------------------------------------------------------------------
 // K2: one radix partition pass.  FIRST=true reads the caller's cloud (any stride), drops
-// invalid / out-of-strip points and tags each survivor with its cloud index in .w;
-// FIRST=false moves already-tagged points between the two work buffers.
+// invalid / out-of-strip points, tags each survivor with its cloud index in .w and builds
+// the digit histograms of ALL later passes (the indices are in registers anyway);
+// FIRST=false moves already-tagged points between the two work buffers and evaluates only
+// the key fields its digit covers (usually one IEEE divide per point instead of three).
 //
-//  1. warp-striped coalesced load, key digit per point
+//  1. all loads of the tile are issued before any dependent work (8 x 512 B in flight per warp)
 //  2. stable in-tile rank: __match_any_sync groups equal digits inside a warp, per-warp
-//     digit counters in shared memory, then a scan across the 8 warps per digit
+//     digit counters in shared memory, then a scan across the 12 warps per digit
 //  3. tile digit counts are published for the decoupled look-back while the points are
 //     reordered into shared memory (so the global writes are runs of equal digits)
 //  4. coalesced copy-out to the digit's global run
 // ---------------------------------------------------------------------------------------
 template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads, 2)
+__global__ void __launch_bounds__(kSortThreads, GNDT_SORT_MINBLOCKS)
 sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_t n_in, size_t start,
-                 const float4 *src, float4 *dst, u32 *lb, const u32 *hist_cur, u32 *hist_next,
-                 DevParams P) {
+                 const float4 *src, float4 *dst, u32 *lb, u32 *hist_all, DevParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SortSmem &S = *reinterpret_cast<SortSmem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -158,9 +173,9 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   const int n_passes = ctl->n_passes;
   if (!FIRST && pass >= n_passes) return;
   if (tid == 0) S.tile_id = atomicAdd(&ctl->ticket[pass], 1u);
-#pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) S.whist[w][tid] = 0;
-  S.next_hist[tid] = 0;
+  for (int i = tid; i < kSortWarps * kRadixBins; i += kSortThreads) (&S.whist[0][0])[i] = 0;
+  if (FIRST)
+    for (int i = tid; i < (kMaxPasses - 1) * kRadixBins; i += kSortThreads) (&S.later_hist[0][0])[i] = 0;
   __syncthreads();
   const int tile = (int)S.tile_id;
   const size_t M = FIRST ? (n_in - start) : (size_t)ctl->n_valid;
@@ -171,14 +186,31 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   const KeyLayout L = load_layout(ctl);
   const int shift = ctl->shift[pass], bits = ctl->bits[pass];
   const u32 mask = (1u << bits) - 1u;
-  const bool has_next = pass + 1 < n_passes;
-  const int nshift = has_next ? ctl->shift[pass + 1] : 0;
-  const u32 nmask = has_next ? ((1u << ctl->bits[pass + 1]) - 1u) : 0u;
   const float o[3] = {ctl->origin[0], ctl->origin[1], ctl->origin[2]};
   const bool tiled = P.tile_lo < P.tile_hi;
   const bool vec = FIRST && (stride_f == 4) && ((reinterpret_cast<uintptr_t>(in_raw) & 15) == 0);
+  // key fields this pass's digit overlaps: z [0,bz), y [bz,bz+by), x [bz+by, ...)
+  const int need = FIRST ? 7
+                         : ((shift + bits > L.bz + L.by ? 1 : 0) | ((shift < L.bz + L.by && shift + bits > L.bz) ? 2 : 0) |
+                            (shift < L.bz ? 4 : 0));
 
+  // ---- 1. loads first
   float4 e[kSortItems];
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const int i = warp * (32 * kSortItems) + k * 32 + lane;
+    if (i < cnt) {
+      if (FIRST) e[k] = load_point(in_raw, stride_f, start + base + i, vec);
+      else e[k] = ld_stream(src + base + i);
+    }
+  }
+  int q_shift[kMaxPasses];
+  u32 q_mask[kMaxPasses];
+#pragma unroll
+  for (int q = 0; q < kMaxPasses; ++q) {
+    q_shift[q] = FIRST ? ctl->shift[q] : 0;
+    q_mask[q] = FIRST ? ((1u << ctl->bits[q]) - 1u) : 0u;
+  }
   u32 dg[kSortItems];
 #pragma unroll
   for (int k = 0; k < kSortItems; ++k) {
@@ -186,26 +218,29 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
     dg[k] = kInvalidDigit;
     if (i < cnt) {
       int cx, cy, cz;
-      bool ok;
       if (FIRST) {
-        const size_t gi = start + base + i;
-        e[k] = load_point(in_raw, stride_f, gi, vec);
-        e[k].w = __uint_as_float((u32)gi);
-        ok = point_indices(e[k].x, e[k].y, e[k].z, o, P.grid_len, P.z_len, cx, cy, cz);
+        e[k].w = __uint_as_float((u32)(start + base + i));
+        bool ok = point_indices(e[k].x, e[k].y, e[k].z, o, P.grid_len, P.z_len, cx, cy, cz);
         if (ok && tiled && (cx < P.tile_lo || cx >= P.tile_hi)) ok = false;
+        if (ok) {
+          dg[k] = first_digit(cz);
+          const u64 key = compact_key(cx, cy, cz, L);
+#pragma unroll
+          for (int q = 1; q < kMaxPasses; ++q)
+            if (q < n_passes) atomicAdd(&S.later_hist[q - 1][(u32)(key >> q_shift[q]) & q_mask[q]], 1u);
+        }
       } else {
-        e[k] = ld_stream(src + base + i);
-        ok = point_indices(e[k].x, e[k].y, e[k].z, o, P.grid_len, P.z_len, cx, cy, cz);
-      }
-      if (ok) {
-        const u64 key = compact_key(cx, cy, cz, L);
-        dg[k] = FIRST ? first_digit(cz) : ((u32)(key >> shift) & mask);
-        if (has_next) atomicAdd(&S.next_hist[(u32)(key >> nshift) & nmask], 1u);
+        point_indices_masked(e[k].x, e[k].y, e[k].z, o, P.grid_len, P.z_len, need, cx, cy, cz);
+        u64 key = 0;
+        if (need & 1) key |= (u64)(u32)(cx - L.cx_min) << (L.by + L.bz);
+        if (need & 2) key |= (u64)(u32)(cy - L.cy_min) << L.bz;
+        if (need & 4) key |= (u64)(u32)(cz - L.cz_bias);
+        dg[k] = (u32)(key >> shift) & mask;
       }
     }
   }
 
-  // ---- stable rank inside the warp's 12x32 block of points
+  // ---- 2. stable rank inside the warp's 8x32 block of points
   u32 rank[kSortItems];
 #pragma unroll
   for (int k = 0; k < kSortItems; ++k) {
@@ -223,19 +258,22 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   }
   __syncthreads();
 
-  // ---- per digit (thread d): scan over the warps, tile count, look-back publication
+  // ---- 3. per digit (thread d < 256): scan over the warps, tile count, publication
   u32 tile_count = 0;
+  u32 *my_word = lb + (size_t)tile * kRadixBins + (tid & (kRadixBins - 1));
+  if (tid < kRadixBins) {
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) {
-    const u32 t = S.whist[w][tid];
-    S.whist[w][tid] = tile_count;
-    tile_count += t;
+    for (int w = 0; w < kSortWarps; ++w) {
+      const u32 t = S.whist[w][tid];
+      S.whist[w][tid] = tile_count;
+      tile_count += t;
+    }
+    st_relaxed(my_word, (tile == 0 ? kFlagIncl : kFlagAgg) | tile_count);
   }
-  u32 *my_word = lb + (size_t)tile * kRadixBins + tid;
-  st_relaxed(my_word, (tile == 0 ? kFlagIncl : kFlagAgg) | tile_count);
-  const u32 toff = block_exclusive_scan_256(tile_count, S.warp_sums, nullptr);
-  S.tile_off[tid] = toff;
-  const u32 digit_base = block_exclusive_scan_256(hist_cur[tid], S.warp_sums, nullptr);
+  // exclusive scans over the 256 digits (threads >= 256 contribute zeros)
+  const u32 toff = block_exclusive_scan(tile_count, S.warp_sums);
+  const u32 digit_base = block_exclusive_scan(tid < kRadixBins ? hist_all[(size_t)pass * kRadixBins + tid] : 0u, S.warp_sums);
+  if (tid < kRadixBins) S.tile_off[tid] = toff;
   __syncthreads();
 
   // ---- reorder into shared memory by digit (stable)
@@ -249,30 +287,46 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   }
 
   // ---- decoupled look-back for digit `tid`
-  u32 prefix = 0;
-  if (tile > 0) {
-    const u32 *p = my_word;
-    for (int j = tile - 1; j >= 0; --j) {
-      p -= kRadixBins;
-      u32 w, spins = 0;
-      do { w = ld_relaxed(p); } while ((w & kFlagMask) == 0 && ++spins < kSpinLimit);
-      if ((w & kFlagMask) == 0) { atomicOr(&ctl->err, kErrWatchdog); break; }
-      prefix += w & kValMask;
-      if (w & kFlagIncl) break;
+  if (tid < kRadixBins) {
+    u32 prefix = 0;
+    if (tile > 0) {
+      // walk back over the predecessors' words, kLookBatch independent loads per round trip
+      constexpr int kLookBatch = 8;
+      bool done = false;
+      for (int j = tile - 1; j >= 0 && !done; j -= kLookBatch) {
+        u32 w[kLookBatch];
+#pragma unroll
+        for (int q = 0; q < kLookBatch; ++q)
+          w[q] = (j - q >= 0) ? ld_relaxed(my_word - (size_t)(tile - (j - q)) * kRadixBins) : kFlagIncl;
+#pragma unroll
+        for (int q = 0; q < kLookBatch; ++q) {
+          if (done) break;
+          u32 spins = 0;
+          while ((w[q] & kFlagMask) == 0 && ++spins < kSpinLimit)
+            w[q] = ld_relaxed(my_word - (size_t)(tile - (j - q)) * kRadixBins);
+          if ((w[q] & kFlagMask) == 0) { atomicOr(&ctl->err, kErrWatchdog); done = true; break; }
+          prefix += w[q] & kValMask;
+          if (w[q] & kFlagIncl) done = true;
+        }
+      }
+      st_relaxed(my_word, kFlagIncl | (prefix + tile_count));
     }
-    st_relaxed(my_word, kFlagIncl | (prefix + tile_count));
+    S.gbase[tid] = digit_base + prefix - toff;
+    if (tid == kRadixBins - 1) S.n_valid_tile = toff + tile_count;
   }
-  S.gbase[tid] = digit_base + prefix - toff;
-  if (tid == kRadixBins - 1) S.warp_sums[0] = toff + tile_count;  // valid points in the tile
   __syncthreads();
 
-  // ---- copy out: consecutive threads write consecutive addresses inside a digit run
-  const int n_valid_tile = (int)S.warp_sums[0];
+  // ---- 4. copy out: consecutive threads write consecutive addresses inside a digit run
+  const int n_valid_tile = (int)S.n_valid_tile;
   for (int i = tid; i < n_valid_tile; i += kSortThreads) {
     const u32 d = S.sdig[i];
     st_stream(dst + S.gbase[d] + i, S.stage[i]);
   }
-  if (has_next && S.next_hist[tid]) atomicAdd(&hist_next[tid], S.next_hist[tid]);
+  if (FIRST)
+    for (int i = tid; i < (n_passes - 1) * kRadixBins; i += kSortThreads) {
+      const u32 c = (&S.later_hist[0][0])[i];
+      if (c) atomicAdd(&hist_all[kRadixBins + i], c);
+    }
 }
 
 }  // namespace gndt
