@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("GNDT_LIB") or os.path.join(HERE, "libgndt.so")  # GNDT_LIB: tuning variants only
 SOURCES = [os.path.join(HERE, "csrc", f) for f in (
-    "gndt_api.cu", "gndt_device.cuh", "gndt_sort.cuh", "gndt_reduce.cuh", "gndt_label.cuh")]
+    "gndt_api.cu", "gndt_device.cuh", "gndt_sort.cuh", "gndt_reduce.cuh", "gndt_label.cuh", "gndt_update.cuh")]
 HEADER = os.path.join(REPO, "include", "gndt.h")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -65,6 +65,9 @@ SYMBOLS = {
     "gndt_count_morton": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "gndt_morton_to_xy": (None, [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "gndt_morton_string": (_i, [C.c_int32, C.c_int32, C.c_char_p]),
+    "gndt_cell_center": (_i, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                              C.POINTER(C.c_float)]),
+    "gndt_origin": (_i, [_vp, C.POINTER(C.c_float)]),
 }
 
 

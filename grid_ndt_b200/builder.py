@@ -218,9 +218,25 @@ class TwoDmap:
         _check(self._h, lib().gndt_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def origin(self):
+        """The map origin in use (TwoDmap::cloudFirst): point 0 of the initial cloud for
+        chatterCallback builds, the setCloudFirst value otherwise."""
+        o = (C.c_float * 3)()
+        _check(self._h, lib().gndt_origin(self._h, o))
+        return np.array(o[:], np.float32)
+
+    def countPositionXYZ(self, sx: int, sy: int, sz: int):
+        """Centre of a cell in metres (map2D.h:918-947)."""
+        o = (C.c_float * 3)(*self.origin())
+        c = (C.c_float * 3)()
+        rc = lib().gndt_cell_center(o, self._p.grid_len, self._p.z_len, int(sx), int(sy), int(sz), c)
+        if rc != 0:
+            raise GndtError(rc, "cell indices are signed and non-zero")
+        return np.array(c[:], np.float32)
+
     def transMortonXYZ(self, position, origin=None):
         """(morton_xy string, morton_z) of a position (map2D.h:950-976)."""
-        o = origin if origin is not None else [self._p.origin[i] for i in range(3)]
+        o = origin if origin is not None else self.origin()
         oo = (C.c_float * 3)(*[np.float32(v) for v in o])
         pp = (C.c_float * 3)(*[np.float32(v) for v in position])
         sx, sy, sz = C.c_int32(), C.c_int32(), C.c_int32()

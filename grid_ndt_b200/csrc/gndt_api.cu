@@ -1,9 +1,10 @@
 // gndt_api.cu — C ABI of libgndt.so (include/gndt.h): handle, device workspace, the fixed
-// launch sequence of one map build, result accessors and the host-side key helpers.
+// launch sequence of one map build / one streaming update, result accessors and the
+// host-side key helpers.
 //
-// One build = bounds -> plan -> up to 6 partition passes -> reduce -> fixup -> label ->
-// column_finish -> edges, all stream-ordered with no host round trip; counts are read
-// back only when the caller asks for them.
+// front end : bounds -> plan -> up to 6 partition passes -> reduce -> fixup   (cloud -> moments)
+// back end  : finalize+label -> column_finish -> edges                        (moments -> tables)
+// All stream-ordered with no host round trip; counts are read back only when asked for.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 #include "gndt_label.cuh"
 #include "gndt_reduce.cuh"
 #include "gndt_sort.cuh"
+#include "gndt_update.cuh"
 
 using namespace gndt;
 
@@ -34,12 +36,16 @@ struct gndt_handle {
   int device = 0;
   gndt_params params;
   std::string err;
-  // workspace
-  Buffer in_stage, buf_a, buf_b, mom, table, slopes, columns, zero;
+  // workspace sized by points
+  Buffer in_stage, buf_a, buf_b, zero;
+  // workspace sized by voxels
+  Buffer mom, mom_alt, table, slopes, columns;
+  // streaming update scratch (sized by the scan)
+  Buffer mom_scan, upd_flags, upd_pos, upd_keys;
+  Buffer small;  // Totals + n_new word, never memset by a build
   size_t cap_points = 0, cap_voxels = 0;
   // carved out of `zero`
   Ctl *ctl = nullptr;
-  Ctl *ctl2 = nullptr;  // scratch control block for gndt_label_edges on foreign tables
   u32 *hist = nullptr;
   u32 *row_start = nullptr, *row_end = nullptr;
   u32 *lb = nullptr;
@@ -48,17 +54,18 @@ struct gndt_handle {
   u64 *blk_state = nullptr;
   size_t zero_bytes_used = 0;
   size_t sort_tiles = 0, red_tiles = 0, label_blocks = 0;
-  // foreign-table scratch
+  // foreign-table scratch (gndt_label_edges)
   Buffer f_slopes, f_columns, f_zero;
   // state
   bool built = false;
   bool counts_valid = false;
   Ctl host_ctl;
-  size_t n_input = 0;
+  Totals host_tot;
   cudaStream_t last_stream = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
   bool timed_h2d = false;
   uint64_t launches = 0;
+  uint64_t total_points = 0;  // points handed to build + updates so far (host copy)
   int sm_count = 148;
 };
 
@@ -83,10 +90,46 @@ int ensure(gndt_handle *h, Buffer &b, size_t bytes) {
   return GNDT_OK;
 }
 
+// grow keeping the first `keep` bytes
+int ensure_keep(gndt_handle *h, Buffer &b, size_t bytes, size_t keep, cudaStream_t st) {
+  if (b.bytes >= bytes) return GNDT_OK;
+  void *np = nullptr;
+  GNDT_CUDA(h, cudaMalloc(&np, bytes));
+  if (b.p && keep) GNDT_CUDA(h, cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, st));
+  if (b.p) { GNDT_CUDA(h, cudaStreamSynchronize(st)); GNDT_CUDA(h, cudaFree(b.p)); }
+  b.p = np;
+  b.bytes = bytes;
+  return GNDT_OK;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Largest non-negative float a with (int)ceil(a / len) <= GNDT_MAX_INDEX, by bisection over
+// the bit patterns (the test is monotone in a).  Same IEEE binary32 operations as the device
+// index arithmetic, so "|p - p0| <= max_abs" is exactly "the point's index is in range".
+float max_abs_offset(float len) {
+  auto ok = [len](uint32_t b) {
+    float a;
+    memcpy(&a, &b, 4);
+    volatile float q = a / len;
+    return std::ceil((float)q) <= (float)GNDT_MAX_INDEX;
+  };
+  uint32_t lo = 0, hi = 0x7f7fffffu;  // 0.0f is always valid; FLT_MAX usually is not
+  if (ok(hi)) lo = hi;
+  while (lo + 1 < hi) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (ok(mid)) lo = mid; else hi = mid;
+  }
+  float a;
+  memcpy(&a, &lo, 4);
+  return a;
+}
 
 DevParams to_dev(const gndt_params &p, size_t cap_voxels) {
   DevParams d;
+  d.max_abs[0] = max_abs_offset(p.grid_len);
+  d.max_abs[1] = max_abs_offset(p.z_len);
+  d.idx_offset = 0;
   d.grid_len = p.grid_len; d.z_len = p.z_len; d.slope_interval = p.slope_interval;
   d.demand = p.demand; d.min_points = p.min_points;
   d.rough_max = p.rough_max; d.angle_max_deg = p.angle_max_deg; d.reach_height = p.reach_height;
@@ -107,17 +150,19 @@ int validate_params(const gndt_params *p) {
   return GNDT_OK;
 }
 
-// Size the workspace for n points and carve the zero-initialised region.
-int reserve(gndt_handle *h, size_t n, bool host_input, size_t stride_bytes) {
-  const size_t cap_vox = h->params.max_voxels ? (size_t)h->params.max_voxels : n;
+// Workspace for n points and cap_vox voxels; carves the zero-initialised region.
+// `keep_mom` bytes of the resident moments survive a regrow (streaming update).
+int reserve(gndt_handle *h, size_t n, size_t cap_vox, bool host_input, size_t stride_bytes, size_t keep_mom,
+            cudaStream_t st) {
   int rc;
   if (host_input && (rc = ensure(h, h->in_stage, n * stride_bytes)) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->buf_a, n * sizeof(float4))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->buf_b, n * sizeof(float4))) != GNDT_OK) return rc;
-  if ((rc = ensure(h, h->mom, cap_vox * sizeof(VoxMoments))) != GNDT_OK) return rc;
+  if ((rc = ensure_keep(h, h->mom, cap_vox * sizeof(VoxMoments), keep_mom, st)) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->table, cap_vox * sizeof(gndt_voxel))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->slopes, cap_vox * sizeof(gndt_slope))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->columns, cap_vox * sizeof(gndt_column))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->small, 256)) != GNDT_OK) return rc;
   h->cap_points = n;
   h->cap_voxels = cap_vox;
   h->sort_tiles = (n + kSortTile - 1) / kSortTile;
@@ -126,7 +171,6 @@ int reserve(gndt_handle *h, size_t n, bool host_input, size_t stride_bytes) {
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_ctl = carve(sizeof(Ctl));
-  const size_t o_ctl2 = carve(sizeof(Ctl));
   const size_t o_hist = carve((kMaxPasses + 1) * kRadixBins * sizeof(u32));
   const size_t o_rs = carve(65536 * sizeof(u32));
   const size_t o_re = carve(65536 * sizeof(u32));
@@ -137,7 +181,6 @@ int reserve(gndt_handle *h, size_t n, bool host_input, size_t stride_bytes) {
   if ((rc = ensure(h, h->zero, off)) != GNDT_OK) return rc;
   char *z = static_cast<char *>(h->zero.p);
   h->ctl = reinterpret_cast<Ctl *>(z + o_ctl);
-  h->ctl2 = reinterpret_cast<Ctl *>(z + o_ctl2);
   h->hist = reinterpret_cast<u32 *>(z + o_hist);
   h->row_start = reinterpret_cast<u32 *>(z + o_rs);
   h->row_end = reinterpret_cast<u32 *>(z + o_re);
@@ -162,18 +205,61 @@ int sync_counts(gndt_handle *h) {
   if (h->counts_valid) return GNDT_OK;
   GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
   GNDT_CUDA(h, cudaMemcpy(&h->host_ctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
-  if (h->host_ctl.err & kErrWatchdog) { h->err = "device watchdog tripped (look-back never resolved)"; return GNDT_ERR_INTERNAL; }
+  GNDT_CUDA(h, cudaMemcpy(&h->host_tot, h->small.p, sizeof(Totals), cudaMemcpyDeviceToHost));
+  if (h->host_ctl.err & kErrWatchdog) { h->err = "device watchdog tripped (look-back / TMA wait never resolved)"; return GNDT_ERR_INTERNAL; }
   if (h->host_ctl.err & kErrCapacity) { h->err = "voxel table capacity (max_voxels) exceeded"; return GNDT_ERR_CAPACITY; }
   h->counts_valid = true;
   return GNDT_OK;
 }
 
-// label -> column_finish -> edges on (table, n) with the handle's own control block.
-int launch_label_and_edges(gndt_handle *h, cudaStream_t st, const DevParams &dp) {
+// cloud -> sorted raw moments in `out` (h->ctl->n_voxels entries)
+int front_end(gndt_handle *h, cudaStream_t st, const float *d_in, size_t n, size_t stride_f, size_t start,
+              const DevParams &dp, VoxMoments *out) {
+  GNDT_CUDA(h, cudaMemsetAsync(h->zero.p, 0, h->zero_bytes_used, st));
+  // K1: bounds + first-digit histogram, then the key layout
+  bounds_kernel<<<grid_for(h, n, 256 * 8, 8), 256, 0, st>>>(h->ctl, h->hist, d_in, stride_f, n, start, dp);
+  plan_kernel<<<1, 32, 0, st>>>(h->ctl);
+  h->launches += 2;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_KEY], st));
+  // K2: partition passes (pass p writes buffer A when p is even, B when odd)
+  const int tiles = (int)((n + kSortTile - 1) / kSortTile);
+  float4 *A = static_cast<float4 *>(h->buf_a.p), *B = static_cast<float4 *>(h->buf_b.p);
+  sort_pass_kernel<true><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A,
+                                                                        h->lb, h->hist, dp);
+  for (int p = 1; p < kMaxPasses; ++p) {
+    const float4 *src = (p & 1) ? A : B;
+    float4 *dst = (p & 1) ? B : A;
+    sort_pass_kernel<false><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
+        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins, h->hist, dp);
+  }
+  h->launches += kMaxPasses;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));
+  // K3: per-voxel moments
+  const int rtiles = (int)((n + kRedTile - 1) / kRedTile);
+  reduce_kernel<<<rtiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, out, h->carry, h->tile_state, dp);
+  fixup_kernel<<<grid_for(h, (size_t)rtiles * 32, 128, 16), 128, 0, st>>>(h->ctl, out, h->carry);
+  h->launches += 2;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_REDUCE], st));
+  return GNDT_OK;
+}
+
+__global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_fixed) {
+  const u32 n = n_fixed ? n_fixed : ctl->n_voxels;
+  if (threadIdx.x == 0 && n && !ctl->err) {
+    ctl->cx_min = contiguous_index(table[0].sx);
+    ctl->cx_max = contiguous_index(table[n - 1].sx);
+  }
+}
+
+// sorted raw moments -> voxel / slope / column tables + reachability bits
+int back_end(gndt_handle *h, cudaStream_t st, const DevParams &dp, const VoxMoments *mom, bool bounds_from_table) {
   const int g_lab = grid_for(h, h->cap_voxels, kLabelThreads, 8);
-  finalize_label_kernel<<<g_lab, kLabelThreads, 0, st>>>(h->ctl, (const VoxMoments *)h->mom.p, (gndt_voxel *)h->table.p,
-                                                         (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p,
-                                                         h->blk_state, &h->ctl->ticket[7], dp);
+  finalize_label_kernel<<<g_lab, kLabelThreads, 0, st>>>(h->ctl, mom, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
+                                                         (gndt_column *)h->columns.p, h->blk_state, &h->ctl->ticket[7], dp);
+  if (bounds_from_table) {
+    table_bounds_kernel<<<1, 32, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, 0u);
+    h->launches += 1;
+  }
   column_finish_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, 0u, (gndt_column *)h->columns.p,
                                               h->row_start, h->row_end, 0, 0);
   h->launches += 2;
@@ -186,11 +272,20 @@ int launch_label_and_edges(gndt_handle *h, cudaStream_t st, const DevParams &dp)
   return GNDT_OK;
 }
 
+int check_cloud_args(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, const char *who) {
+  if (!xyz || n == 0 || stride_bytes < 12 || (stride_bytes & 3) || (mem != GNDT_MEM_HOST && mem != GNDT_MEM_DEVICE)) {
+    h->err = std::string(who) + ": bad argument (xyz NULL, n == 0, stride not a multiple of 4 >= 12, or bad mem)";
+    return GNDT_ERR_INVALID_ARG;
+  }
+  if (n > GNDT_MAX_POINTS) { h->err = std::string(who) + ": n exceeds GNDT_MAX_POINTS"; return GNDT_ERR_CAPACITY; }
+  return GNDT_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-const char *gndt_version(void) { return "gndt 0.1 (abi 1, sm_100a)"; }
+const char *gndt_version(void) { return "gndt 0.2 (abi 1, sm_100a)"; }
 
 const char *gndt_last_error(const gndt_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -232,7 +327,8 @@ int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
 int gndt_destroy(gndt_handle *h) {
   if (!h) return GNDT_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
-  Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->mom, &h->table, &h->slopes, &h->columns, &h->zero,
+  Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
+                    &h->columns, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small,
                     &h->f_slopes, &h->f_columns, &h->f_zero};
   for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
   for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -248,17 +344,15 @@ int gndt_set_params(gndt_handle *h, const gndt_params *params) {
 
 int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
   if (!h) return GNDT_ERR_INVALID_ARG;
-  if (!xyz || n == 0 || stride_bytes < 12 || (stride_bytes & 3) || (mem != GNDT_MEM_HOST && mem != GNDT_MEM_DEVICE)) {
-    h->err = "gndt_build: bad argument (xyz NULL, n == 0, stride not a multiple of 4 >= 12, or bad mem)";
-    return GNDT_ERR_INVALID_ARG;
-  }
-  if (n > GNDT_MAX_POINTS) { h->err = "gndt_build: n exceeds GNDT_MAX_POINTS"; return GNDT_ERR_CAPACITY; }
+  int rc = check_cloud_args(h, xyz, n, stride_bytes, mem, "gndt_build");
+  if (rc != GNDT_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GNDT_CUDA(h, cudaSetDevice(h->device));
   h->built = false;
   h->counts_valid = false;
   h->launches = 0;
-  int rc = reserve(h, n, mem == GNDT_MEM_HOST, stride_bytes);
+  const size_t cap_vox = h->params.max_voxels ? (size_t)h->params.max_voxels : n;
+  rc = reserve(h, n, cap_vox, mem == GNDT_MEM_HOST, stride_bytes, 0, st);
   if (rc != GNDT_OK) return rc;
 
   const float *d_in = static_cast<const float *>(xyz);
@@ -269,54 +363,87 @@ int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, i
     d_in = static_cast<const float *>(h->in_stage.p);
     h->timed_h2d = true;
   }
-  const size_t stride_f = stride_bytes / 4;
   const size_t start = h->params.origin_is_first_point ? 1 : 0;
   const DevParams dp = to_dev(h->params, h->cap_voxels);
 
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
-  GNDT_CUDA(h, cudaMemsetAsync(h->zero.p, 0, h->zero_bytes_used, st));
-
-  // K1: bounds + first-digit histogram, then the key layout
-  bounds_kernel<<<grid_for(h, n, 256 * 8, 8), 256, 0, st>>>(h->ctl, h->hist, d_in, stride_f, n, start, dp);
-  plan_kernel<<<1, 32, 0, st>>>(h->ctl);
-  h->launches += 2;
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_KEY], st));
-
-  // K2: partition passes (pass p writes buffer A when p is even, B when odd)
-  const int tiles = (int)h->sort_tiles;
-  float4 *A = static_cast<float4 *>(h->buf_a.p), *B = static_cast<float4 *>(h->buf_b.p);
-  sort_pass_kernel<true><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A,
-                                                                        h->lb, h->hist, dp);
-  for (int p = 1; p < kMaxPasses; ++p) {
-    const float4 *src = (p & 1) ? A : B;
-    float4 *dst = (p & 1) ? B : A;
-    sort_pass_kernel<false><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
-        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins, h->hist, dp);
-  }
-  h->launches += kMaxPasses;
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));
-
-  // K3: per-voxel fit
-  reduce_kernel<<<(int)h->red_tiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, (VoxMoments *)h->mom.p,
-                                                                         h->carry, h->tile_state, dp);
-  fixup_kernel<<<grid_for(h, h->red_tiles * 32, 128, 16), 128, 0, st>>>(h->ctl, (VoxMoments *)h->mom.p, h->carry);
-  h->launches += 2;
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_REDUCE], st));
-
-  // K4/K5
-  rc = launch_label_and_edges(h, st, dp);
+  rc = front_end(h, st, d_in, n, stride_bytes / 4, start, dp, (VoxMoments *)h->mom.p);
+  if (rc != GNDT_OK) return rc;
+  totals_kernel<<<1, 32, 0, st>>>((Totals *)h->small.p, h->ctl, (u64)n, 1);
+  h->launches += 1;
+  rc = back_end(h, st, dp, (const VoxMoments *)h->mom.p, false);
   if (rc != GNDT_OK) return rc;
   GNDT_CUDA(h, cudaGetLastError());
   h->built = true;
-  h->n_input = n;
+  h->total_points = n;
   h->last_stream = st;
   return GNDT_OK;
 }
 
-int gndt_update(gndt_handle *h, const void *, size_t, size_t, int, void *) {
+int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
   if (!h) return GNDT_ERR_INVALID_ARG;
-  h->err = "gndt_update: streaming merge is not available in this build";
-  return GNDT_ERR_STATE;
+  int rc = check_cloud_args(h, xyz, n, stride_bytes, mem, "gndt_update");
+  if (rc != GNDT_OK) return rc;
+  // like the reference (map2D.h:679-680: change2DMap returns false on an empty map) an
+  // update needs a resident map; its origin and parameters are kept
+  if ((rc = sync_counts(h)) != GNDT_OK) return rc;
+  if (h->total_points + n > 0xFFFFFFFFull) { h->err = "gndt_update: more than 2^32 points fused"; return GNDT_ERR_CAPACITY; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  const u32 n_res = h->host_ctl.n_voxels;
+  const float origin[3] = {h->host_ctl.origin[0], h->host_ctl.origin[1], h->host_ctl.origin[2]};
+  h->counts_valid = false;
+  h->launches = 0;
+
+  // capacity: every scan point could open a new voxel
+  size_t cap_vox = h->cap_voxels;
+  const size_t need = (size_t)n_res + n;
+  if (h->params.max_voxels == 0 && need > cap_vox) cap_vox = need + need / 2;
+  rc = reserve(h, n > h->cap_points ? n : h->cap_points, cap_vox, mem == GNDT_MEM_HOST, stride_bytes,
+               (size_t)n_res * sizeof(VoxMoments), st);
+  if (rc != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->mom_alt, cap_vox * sizeof(VoxMoments))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->mom_scan, n * sizeof(VoxMoments))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->upd_flags, n * sizeof(u32))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->upd_pos, n * sizeof(u32))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->upd_keys, n * sizeof(u64))) != GNDT_OK) return rc;
+
+  const float *d_in = static_cast<const float *>(xyz);
+  h->timed_h2d = false;
+  if (mem == GNDT_MEM_HOST) {
+    GNDT_CUDA(h, cudaEventRecord(h->ev[EV_H2D0], st));
+    GNDT_CUDA(h, cudaMemcpyAsync(h->in_stage.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, st));
+    d_in = static_cast<const float *>(h->in_stage.p);
+    h->timed_h2d = true;
+  }
+  gndt_params p = h->params;  // every point of the scan is binned against the resident origin
+  p.origin_is_first_point = 0;
+  p.origin[0] = origin[0]; p.origin[1] = origin[1]; p.origin[2] = origin[2];
+  DevParams dp = to_dev(p, cap_vox);
+  dp.idx_offset = (u32)h->total_points;
+
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
+  VoxMoments *res = (VoxMoments *)h->mom.p, *scan = (VoxMoments *)h->mom_scan.p, *merged = (VoxMoments *)h->mom_alt.p;
+  rc = front_end(h, st, d_in, n, stride_bytes / 4, 0, dp, scan);
+  if (rc != GNDT_OK) return rc;
+  totals_kernel<<<1, 32, 0, st>>>((Totals *)h->small.p, h->ctl, (u64)n, 0);
+  u32 *n_new = reinterpret_cast<u32 *>(static_cast<char *>(h->small.p) + 128);
+  const int g_scan = grid_for(h, n, 256, 8), g_res = grid_for(h, n_res, 256, 8);
+  update_match_kernel<<<g_scan, 256, 0, st>>>(h->ctl, res, n_res, scan, (u32 *)h->upd_flags.p);
+  update_compact_kernel<<<1, 1024, 0, st>>>(h->ctl, scan, (const u32 *)h->upd_flags.p, (u32 *)h->upd_pos.p,
+                                            (u64 *)h->upd_keys.p, n_new);
+  update_prepare_backend_kernel<<<1, 32, 0, st>>>(h->ctl, n_res, n_new);
+  update_merge_resident_kernel<<<g_res, 256, 0, st>>>(res, n_res, (const u64 *)h->upd_keys.p, n_new, merged);
+  update_merge_new_kernel<<<g_scan, 256, 0, st>>>(h->ctl, res, n_res, scan, (const u32 *)h->upd_flags.p,
+                                                  (const u32 *)h->upd_pos.p, n_new, merged, (u32)cap_vox);
+  h->launches += 6;
+  rc = back_end(h, st, dp, merged, true);
+  if (rc != GNDT_OK) return rc;
+  GNDT_CUDA(h, cudaGetLastError());
+  std::swap(h->mom, h->mom_alt);
+  h->total_points += n;
+  h->last_stream = st;
+  return GNDT_OK;
 }
 
 int gndt_counts(gndt_handle *h, gndt_counts_t *out) {
@@ -324,10 +451,10 @@ int gndt_counts(gndt_handle *h, gndt_counts_t *out) {
   int rc = sync_counts(h);
   if (rc != GNDT_OK) return rc;
   const Ctl &c = h->host_ctl;
-  out->n_input = h->n_input;
-  out->n_binned = c.n_valid;
-  out->n_dropped = c.n_dropped;
-  out->n_outside_tile = c.n_outside;
+  out->n_input = h->host_tot.n_points;
+  out->n_binned = h->host_tot.n_valid;
+  out->n_dropped = h->host_tot.n_dropped;
+  out->n_outside_tile = h->host_tot.n_outside;
   out->n_columns = c.n_columns;
   out->n_voxels = c.n_voxels;
   out->n_fitted = c.n_fitted;
@@ -370,13 +497,6 @@ int gndt_device_voxels(gndt_handle *h, const gndt_voxel **dptr, size_t *n) {
   *dptr = static_cast<const gndt_voxel *>(h->table.p);
   *n = h->host_ctl.n_voxels;
   return GNDT_OK;
-}
-
-__global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n) {
-  if (threadIdx.x == 0 && n) {
-    ctl->cx_min = contiguous_index(table[0].sx);
-    ctl->cx_max = contiguous_index(table[n - 1].sx);
-  }
 }
 
 int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin, size_t count, void *stream) {
@@ -518,6 +638,26 @@ int gndt_morton_string(int32_t sx, int32_t sy, char *buf) {
   if (!buf) return 0;
   const char q = sx > 0 ? (sy > 0 ? 'A' : 'B') : (sy > 0 ? 'C' : 'D');
   return snprintf(buf, 16, "%c%d", q, (int)gndt_count_morton((uint32_t)abs(sx), (uint32_t)abs(sy)));
+}
+
+/* TwoDmap::countPositionXYZ (include/map2D.h:918-947): centre of a cell, in metres, with the
+ * reference's own float/double mix ((a - 0.5) is double, * gridLen float->double, + origin). */
+int gndt_cell_center(const float origin[3], float grid_len, float z_len, int32_t sx, int32_t sy, int32_t sz,
+                     float center[3]) {
+  if (!origin || !center || sx == 0 || sy == 0 || sz == 0) return GNDT_ERR_INVALID_ARG;
+  const double ax = (std::abs(sx) - 0.5) * grid_len, ay = (std::abs(sy) - 0.5) * grid_len, az = (std::abs(sz) - 0.5) * z_len;
+  center[0] = (float)(sx > 0 ? ax + origin[0] : origin[0] - ax);
+  center[1] = (float)(sy > 0 ? ay + origin[1] : origin[1] - ay);
+  center[2] = (float)(sz > 0 ? origin[2] + az : origin[2] - az);
+  return GNDT_OK;
+}
+
+int gndt_origin(gndt_handle *h, float origin[3]) {
+  if (!h || !origin) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  for (int i = 0; i < 3; ++i) origin[i] = h->host_ctl.origin[i];
+  return GNDT_OK;
 }
 
 }  // extern "C"

@@ -98,13 +98,16 @@ label_kernel(Ctl *ctl, gndt_voxel *table, u32 n_table_fixed, gndt_slope *slopes,
     u32 total = 0;
     const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
     const u32 exc = block_exclusive_scan_256(packed, warp_sums, &total);
-    if (tid == 0) {
+    if (tid < 32) {  // warp 0 resolves the (columns, slopes) prefix of this block, 32 blocks per round trip
       const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
-      s_prefix = lookback_u64(blk_state + blk, (int)blk, mine, &ctl->err);
-      if (blk == n_blocks - 1) {
-        const u64 incl = s_prefix + mine;
-        ctl->n_columns = (u32)(incl >> 31);
-        ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
+      const u64 pre = warp_lookback_u64(blk_state, (int)blk, mine, &ctl->err);
+      if (tid == 0) {
+        s_prefix = pre;
+        if (blk == n_blocks - 1) {
+          const u64 incl = pre + mine;
+          ctl->n_columns = (u32)(incl >> 31);
+          ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
+        }
       }
     }
     const u32 fitted_cnt = __syncthreads_count(live && (flags & GNDT_F_FITTED));
@@ -146,7 +149,7 @@ label_kernel(Ctl *ctl, gndt_voxel *table, u32 n_table_fixed, gndt_slope *slopes,
 //   * label it — the isSlope / countUp rules restated above, against the adjacent records
 //   * compact Slopes and Cells — CTA scan + decoupled look-back over (columns, slopes)
 // and write the 96-byte record exactly once.
-__global__ void __launch_bounds__(kLabelThreads)
+__global__ void __launch_bounds__(kLabelThreads, 3)
 finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_slope *slopes,
                       gndt_column *columns, u64 *blk_state, u32 *counters, DevParams P) {
   __shared__ u32 warp_sums[8];
@@ -242,13 +245,16 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
     const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
     u32 total = 0;
     const u32 exc = block_exclusive_scan_256(packed, warp_sums, &total);
-    if (tid == 0) {
+    if (tid < 32) {  // warp 0 resolves the (columns, slopes) prefix of this block, 32 blocks per round trip
       const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
-      s_prefix = lookback_u64(blk_state + blk, (int)blk, mine, &ctl->err);
-      if (blk == n_blocks - 1) {
-        const u64 incl = s_prefix + mine;
-        ctl->n_columns = (u32)(incl >> 31);
-        ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
+      const u64 pre = warp_lookback_u64(blk_state, (int)blk, mine, &ctl->err);
+      if (tid == 0) {
+        s_prefix = pre;
+        if (blk == n_blocks - 1) {
+          const u64 incl = pre + mine;
+          ctl->n_columns = (u32)(incl >> 31);
+          ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
+        }
       }
     }
     const u32 fitted_cnt = __syncthreads_count(live && (flags & GNDT_F_FITTED));

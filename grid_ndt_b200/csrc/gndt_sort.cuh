@@ -8,8 +8,11 @@
 // run of voxels ordered by z.  Stability gives `first_index` (the first-seen order that
 // the reference's isSlope depends on) for free.
 //
-// Traffic per pass: read 16 B + write 16 B per point (one sweep, decoupled look-back), the
-// digit histogram of pass p+1 is accumulated while pass p moves the data.
+// Traffic per pass: read 16 B + write 16 B per point (one sweep, decoupled look-back).
+// A tile (3072 points, 48 KB) is brought into shared memory by ONE TMA bulk copy
+// (cp.async.bulk, completion on an mbarrier) and never passes through registers as a
+// whole: threads read the one or two coordinates their digit needs, rank, write a 4-byte
+// permutation entry, and the copy-out gathers 16-byte points through it.
 #pragma once
 #include "gndt_device.cuh"
 
@@ -22,24 +25,48 @@ namespace gndt {
 #define GNDT_SORT_ITEMS 8
 #endif
 #ifndef GNDT_SORT_MINBLOCKS
-#define GNDT_SORT_MINBLOCKS 2
+#define GNDT_SORT_MINBLOCKS 3
 #endif
 constexpr int kSortThreads = GNDT_SORT_THREADS;
 constexpr int kSortItems = GNDT_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 3072 points = 48 KB staged
 constexpr int kSortWarps = kSortThreads / 32;
+static_assert(kSortThreads >= kRadixBins && kSortTile <= 65536, "tile shape");
 
-struct SortSmem {
-  float4 stage[kSortTile];
-  unsigned short sdig[kSortTile];
+struct __align__(128) SortSmem {
+  float4 in[kSortTile];            // the tile, in arrival order (TMA destination)
+  u32 slot[kSortTile];             // digit << 16 | source position, in digit order; pass 0 first
+                                   // uses this space for the histograms of the later digits
   u32 whist[kSortWarps][kRadixBins];
   u32 tile_off[kRadixBins];
   u32 gbase[kRadixBins];
-  u32 later_hist[kMaxPasses - 1][kRadixBins];  // pass 0 only: digit histograms of passes 1..5
   u32 warp_sums[16];
+  unsigned long long mbar;
   u32 tile_id;
   u32 n_valid_tile;
 };
+static_assert((kMaxPasses - 1) * kRadixBins <= kSortTile, "later-digit histograms alias slot[]");
+
+// ---- TMA bulk copy + mbarrier (sm_90+; a lone CTA is a cluster of one) ------------------
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, u32 bytes, unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, u32 parity) {
+  for (u32 spins = 0; spins < kSpinLimit; ++spins) {
+    u32 done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
 
 // Load point i of a strided cloud (first 12 bytes of each record are x,y,z).
 __device__ __forceinline__ float4 load_point(const float *in, size_t stride_f, size_t i, bool vec) {
@@ -49,15 +76,18 @@ __device__ __forceinline__ float4 load_point(const float *in, size_t stride_f, s
 }
 
 // ---------------------------------------------------------------------------------------
-// K1a: bounds of the contiguous indices + histogram of the (bounds-independent) first
-// digit + validity counters.  transMortonXYZ arithmetic (map2D.h:950-973) happens here
-// for the first time; pass 0 repeats it bit-identically.
+// K1a: bounds + histogram of the (bounds-independent) first digit + validity counters.
+// The index map of transMortonXYZ (map2D.h:950-973) is monotone in each coordinate, so the
+// index bounds are the indices of the coordinate bounds: this pass keeps min/max of the raw
+// floats of valid points and divides only for the z index (the first digit).  A point is
+// valid iff |p - p0| <= P.max_abs[axis], the largest offset whose index is <= GNDT_MAX_INDEX
+// (found on the host with the same IEEE operations).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bounds_kernel(Ctl *ctl, u32 *hist0, const float *in,
                                                      size_t stride_f, size_t n_in, size_t start,
                                                      DevParams P) {
   __shared__ u32 sh[kRadixBins];
-  __shared__ int red[6][8];
+  __shared__ float red[6][8];
   __shared__ u32 cnt[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool vec = (stride_f == 4) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
@@ -69,39 +99,48 @@ __global__ void __launch_bounds__(256) bounds_kernel(Ctl *ctl, u32 *hist0, const
   if (tid < 3) cnt[tid] = 0;
   __syncthreads();
   const bool tiled = P.tile_lo < P.tile_hi;
-  int mx = -kIdxBias, my = -kIdxBias, mz = -kIdxBias, nx = -kIdxBias, ny = -kIdxBias, nz = -kIdxBias;
+  const float inf = __int_as_float(0x7f800000);
+  float lo_x = inf, lo_y = inf, lo_z = inf, hi_x = -inf, hi_y = -inf, hi_z = -inf;
   u32 n_ok = 0, n_drop = 0, n_out = 0;
   for (size_t i = start + (size_t)blockIdx.x * blockDim.x + tid; i < n_in; i += (size_t)gridDim.x * blockDim.x) {
-    float4 p = load_point(in, stride_f, i, vec);
-    int cx, cy, cz;
-    if (!point_indices(p.x, p.y, p.z, o, P.grid_len, P.z_len, cx, cy, cz)) { n_drop++; continue; }
-    if (tiled && (cx < P.tile_lo || cx >= P.tile_hi)) { n_out++; continue; }
-    n_ok++;
-    mx = max(mx, cx); my = max(my, cy); mz = max(mz, cz);
-    nx = max(nx, -cx); ny = max(ny, -cy); nz = max(nz, -cz);
-    {  // warp-aggregated: flat scenes put most of a warp into one z bin
-      const u32 d = first_digit(cz);
-      const u32 peers = __match_any_sync(__activemask(), d);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[d], (u32)__popc(peers));
+    const float4 p = load_point(in, stride_f, i, vec);
+    const bool ok = fabsf(__fsub_rn(p.x, o[0])) <= P.max_abs[0] && fabsf(__fsub_rn(p.y, o[1])) <= P.max_abs[0] &&
+                    fabsf(__fsub_rn(p.z, o[2])) <= P.max_abs[1];
+    if (!ok) { n_drop++; continue; }  // NaN / Inf / out of the supported index range
+    if (tiled) {
+      int cx;
+      axis_index(p.x, o[0], P.grid_len, cx);
+      if (cx < P.tile_lo || cx >= P.tile_hi) { n_out++; continue; }
     }
+    n_ok++;
+    lo_x = fminf(lo_x, p.x); lo_y = fminf(lo_y, p.y); lo_z = fminf(lo_z, p.z);
+    hi_x = fmaxf(hi_x, p.x); hi_y = fmaxf(hi_y, p.y); hi_z = fmaxf(hi_z, p.z);
+    int cz;
+    axis_index(p.z, o[2], P.z_len, cz);
+    const u32 d = first_digit(cz);
+    const u32 peers = __match_any_sync(__activemask(), d);  // flat scenes: most lanes share a z bin
+    if (lane == __ffs(peers) - 1) atomicAdd(&sh[d], (u32)__popc(peers));
   }
 #pragma unroll
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o2)); my = max(my, __shfl_xor_sync(0xffffffffu, my, o2));
-    mz = max(mz, __shfl_xor_sync(0xffffffffu, mz, o2)); nx = max(nx, __shfl_xor_sync(0xffffffffu, nx, o2));
-    ny = max(ny, __shfl_xor_sync(0xffffffffu, ny, o2)); nz = max(nz, __shfl_xor_sync(0xffffffffu, nz, o2));
+    lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o2)); lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o2));
+    lo_z = fminf(lo_z, __shfl_xor_sync(0xffffffffu, lo_z, o2)); hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o2));
+    hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o2)); hi_z = fmaxf(hi_z, __shfl_xor_sync(0xffffffffu, hi_z, o2));
     n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o2); n_drop += __shfl_xor_sync(0xffffffffu, n_drop, o2);
     n_out += __shfl_xor_sync(0xffffffffu, n_out, o2);
   }
   if (lane == 0) {
-    red[0][warp] = mx; red[1][warp] = my; red[2][warp] = mz; red[3][warp] = nx; red[4][warp] = ny; red[5][warp] = nz;
+    red[0][warp] = hi_x; red[1][warp] = hi_y; red[2][warp] = hi_z; red[3][warp] = lo_x; red[4][warp] = lo_y; red[5][warp] = lo_z;
     atomicAdd(&cnt[0], n_ok); atomicAdd(&cnt[1], n_drop); atomicAdd(&cnt[2], n_out);
   }
   __syncthreads();
-  if (tid < 6) {
-    int m = red[tid][0];
-    for (int w = 1; w < 8; ++w) m = max(m, red[tid][w]);
-    if (cnt[0]) atomicMax(&ctl->max_cx_b + tid, (u32)(m + kIdxBias));
+  if (tid < 6 && cnt[0]) {
+    float m = red[tid][0];
+    for (int w = 1; w < 8; ++w) m = (tid < 3) ? fmaxf(m, red[tid][w]) : fminf(m, red[tid][w]);
+    const int ax = tid % 3;
+    int c;
+    axis_index(m, o[ax], ax == 2 ? P.z_len : P.grid_len, c);  // index of the extreme coordinate
+    atomicMax(&ctl->max_cx_b + tid, (u32)((tid < 3 ? c : -c) + kIdxBias));
   }
   if (tid == 0) {
     if (cnt[0]) atomicAdd(&ctl->n_valid, (u64)cnt[0]);
@@ -151,31 +190,39 @@ __global__ void plan_kernel(Ctl *ctl) {
 // ---------------------------------------------------------------------------------------
 // K2: one radix partition pass.  FIRST=true reads the caller's cloud (any stride), drops
 // invalid / out-of-strip points, tags each survivor with its cloud index in .w and builds
-// the digit histograms of ALL later passes (the indices are in registers anyway);
-// FIRST=false moves already-tagged points between the two work buffers and evaluates only
-// the key fields its digit covers (usually one IEEE divide per point instead of three).
+// the digit histograms of ALL later passes; FIRST=false moves already-tagged points between
+// the two work buffers and evaluates only the key fields its digit covers (usually one IEEE
+// divide per point instead of three).
 //
-//  1. all loads of the tile are issued before any dependent work (8 x 512 B in flight per warp)
+//  1. the tile is fetched into shared memory by one TMA bulk copy (strided / unaligned
+//     caller clouds fall back to per-thread loads)
 //  2. stable in-tile rank: __match_any_sync groups equal digits inside a warp, per-warp
-//     digit counters in shared memory, then a scan across the 12 warps per digit
-//  3. tile digit counts are published for the decoupled look-back while the points are
-//     reordered into shared memory (so the global writes are runs of equal digits)
-//  4. coalesced copy-out to the digit's global run
+//     digit counters in shared memory, then a scan across the warps per digit
+//  3. tile digit counts are published for the decoupled look-back while the permutation
+//     (digit, source position) is written in digit order
+//  4. copy-out: consecutive threads gather their point through the permutation and write
+//     consecutive addresses inside a digit run
 // ---------------------------------------------------------------------------------------
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads, GNDT_SORT_MINBLOCKS)
 sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_t n_in, size_t start,
                  const float4 *src, float4 *dst, u32 *lb, u32 *hist_all, DevParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SortSmem &S = *reinterpret_cast<SortSmem *>(smem_raw);
+  extern __shared__ __align__(128) unsigned char smem_sort[];
+  SortSmem &S = *reinterpret_cast<SortSmem *>(smem_sort);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   const int n_passes = ctl->n_passes;
   if (!FIRST && pass >= n_passes) return;
-  if (tid == 0) S.tile_id = atomicAdd(&ctl->ticket[pass], 1u);
-  for (int i = tid; i < kSortWarps * kRadixBins; i += kSortThreads) (&S.whist[0][0])[i] = 0;
+  if (tid == 0) {
+    S.tile_id = atomicAdd(&ctl->ticket[pass], 1u);
+    mbar_init(&S.mbar, 1);
+  }
+  const int bits = ctl->bits[pass];
+  const int n_bins = 1 << bits;  // digits of this pass: 256 or fewer
+  for (int i = tid; i < (kSortWarps << bits); i += kSortThreads) S.whist[i >> bits][i & (n_bins - 1)] = 0;
+  u32 *later_hist = S.slot;  // [kMaxPasses-1][256], pass 0 only
   if (FIRST)
-    for (int i = tid; i < (kMaxPasses - 1) * kRadixBins; i += kSortThreads) (&S.later_hist[0][0])[i] = 0;
+    for (int i = tid; i < (n_passes - 1) * kRadixBins; i += kSortThreads) later_hist[i] = 0;
   __syncthreads();
   const int tile = (int)S.tile_id;
   const size_t M = FIRST ? (n_in - start) : (size_t)ctl->n_valid;
@@ -183,27 +230,31 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   if (base >= M) return;
   const int cnt = (int)min((size_t)kSortTile, M - base);
 
+  // ---- 1. tile -> shared memory
+  const bool vec = !FIRST || ((stride_f == 4) && ((reinterpret_cast<uintptr_t>(in_raw) & 15) == 0));
+  if (vec) {
+    if (tid == 0) {
+      const float4 *g = FIRST ? reinterpret_cast<const float4 *>(in_raw) + start + base : src + base;
+      tma_load_1d(S.in, g, (u32)cnt * 16u, &S.mbar);
+    }
+  } else {
+    for (int i = tid; i < cnt; i += kSortThreads) S.in[i] = load_point(in_raw, stride_f, start + base + i, false);
+  }
+
   const KeyLayout L = load_layout(ctl);
-  const int shift = ctl->shift[pass], bits = ctl->bits[pass];
+  const int shift = ctl->shift[pass];
   const u32 mask = (1u << bits) - 1u;
+  // digit = OR over the fields of ((field >> rs) << ls), all 32-bit: a field at key offset
+  // `off` contributes its bits [shift-off, ...) when off <= shift, else lands at off-shift
+  const int off_y = L.bz, off_x = L.bz + L.by;
+  const int rs_z = shift, rs_y = max(shift - off_y, 0), ls_y = max(off_y - shift, 0);
+  const int rs_x = max(shift - off_x, 0), ls_x = max(off_x - shift, 0);
   const float o[3] = {ctl->origin[0], ctl->origin[1], ctl->origin[2]};
   const bool tiled = P.tile_lo < P.tile_hi;
-  const bool vec = FIRST && (stride_f == 4) && ((reinterpret_cast<uintptr_t>(in_raw) & 15) == 0);
   // key fields this pass's digit overlaps: z [0,bz), y [bz,bz+by), x [bz+by, ...)
   const int need = FIRST ? 7
                          : ((shift + bits > L.bz + L.by ? 1 : 0) | ((shift < L.bz + L.by && shift + bits > L.bz) ? 2 : 0) |
                             (shift < L.bz ? 4 : 0));
-
-  // ---- 1. loads first
-  float4 e[kSortItems];
-#pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
-    const int i = warp * (32 * kSortItems) + k * 32 + lane;
-    if (i < cnt) {
-      if (FIRST) e[k] = load_point(in_raw, stride_f, start + base + i, vec);
-      else e[k] = ld_stream(src + base + i);
-    }
-  }
   int q_shift[kMaxPasses];
   u32 q_mask[kMaxPasses];
 #pragma unroll
@@ -211,31 +262,39 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
     q_shift[q] = FIRST ? ctl->shift[q] : 0;
     q_mask[q] = FIRST ? ((1u << ctl->bits[q]) - 1u) : 0u;
   }
+
+  if (vec) {
+    if (!mbar_wait(&S.mbar, 0)) atomicOr(&ctl->err, kErrWatchdog);
+  } else {
+    __syncthreads();
+  }
+
+  // ---- digits
   u32 dg[kSortItems];
 #pragma unroll
   for (int k = 0; k < kSortItems; ++k) {
     const int i = warp * (32 * kSortItems) + k * 32 + lane;
     dg[k] = kInvalidDigit;
     if (i < cnt) {
+      const float4 e = S.in[i];
       int cx, cy, cz;
       if (FIRST) {
-        e[k].w = __uint_as_float((u32)(start + base + i));
-        bool ok = point_indices(e[k].x, e[k].y, e[k].z, o, P.grid_len, P.z_len, cx, cy, cz);
+        bool ok = point_indices(e.x, e.y, e.z, o, P.grid_len, P.z_len, cx, cy, cz);
         if (ok && tiled && (cx < P.tile_lo || cx >= P.tile_hi)) ok = false;
         if (ok) {
           dg[k] = first_digit(cz);
           const u64 key = compact_key(cx, cy, cz, L);
 #pragma unroll
           for (int q = 1; q < kMaxPasses; ++q)
-            if (q < n_passes) atomicAdd(&S.later_hist[q - 1][(u32)(key >> q_shift[q]) & q_mask[q]], 1u);
+            if (q < n_passes) atomicAdd(&later_hist[(q - 1) * kRadixBins + ((u32)(key >> q_shift[q]) & q_mask[q])], 1u);
         }
       } else {
-        point_indices_masked(e[k].x, e[k].y, e[k].z, o, P.grid_len, P.z_len, need, cx, cy, cz);
-        u64 key = 0;
-        if (need & 1) key |= (u64)(u32)(cx - L.cx_min) << (L.by + L.bz);
-        if (need & 2) key |= (u64)(u32)(cy - L.cy_min) << L.bz;
-        if (need & 4) key |= (u64)(u32)(cz - L.cz_bias);
-        dg[k] = (u32)(key >> shift) & mask;
+        point_indices_masked(e.x, e.y, e.z, o, P.grid_len, P.z_len, need, cx, cy, cz);
+        u32 d = 0;
+        if (need & 1) d |= ((u32)(cx - L.cx_min) >> rs_x) << ls_x;
+        if (need & 2) d |= ((u32)(cy - L.cy_min) >> rs_y) << ls_y;
+        if (need & 4) d |= (u32)(cz - L.cz_bias) >> rs_z;
+        dg[k] = d & mask;
       }
     }
   }
@@ -258,10 +317,22 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   }
   __syncthreads();
 
+  // pass 0: the histograms of the later digits leave shared memory before slot[] reuses it
+  if (FIRST) {
+    for (int i = tid; i < (n_passes - 1) * kRadixBins; i += kSortThreads) {
+      const u32 c = later_hist[i];
+      if (c) atomicAdd(&hist_all[kRadixBins + i], c);
+    }
+  }
+
   // ---- 3. per digit (thread d < 256): scan over the warps, tile count, publication
+  // A digit takes part only if it exists in this pass (tid < n_bins) and some point of the
+  // cloud has it (global count != 0): empty z levels / narrow digits cost no look-back.
   u32 tile_count = 0;
   u32 *my_word = lb + (size_t)tile * kRadixBins + (tid & (kRadixBins - 1));
-  if (tid < kRadixBins) {
+  const u32 global_count = (tid < n_bins) ? hist_all[(size_t)pass * kRadixBins + tid] : 0u;
+  const bool live_digit = global_count != 0;
+  if (live_digit) {
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       const u32 t = S.whist[w][tid];
@@ -270,26 +341,25 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
     }
     st_relaxed(my_word, (tile == 0 ? kFlagIncl : kFlagAgg) | tile_count);
   }
-  // exclusive scans over the 256 digits (threads >= 256 contribute zeros)
+  // exclusive scans over the digits (other threads contribute zeros)
   const u32 toff = block_exclusive_scan(tile_count, S.warp_sums);
-  const u32 digit_base = block_exclusive_scan(tid < kRadixBins ? hist_all[(size_t)pass * kRadixBins + tid] : 0u, S.warp_sums);
+  const u32 digit_base = block_exclusive_scan(global_count, S.warp_sums);
   if (tid < kRadixBins) S.tile_off[tid] = toff;
-  __syncthreads();
+  __syncthreads();  // also orders the later_hist reads above before the slot[] writes below
 
-  // ---- reorder into shared memory by digit (stable)
+  // ---- permutation in digit order (stable)
 #pragma unroll
   for (int k = 0; k < kSortItems; ++k) {
     if (dg[k] != kInvalidDigit) {
       const u32 pos = S.tile_off[dg[k]] + S.whist[warp][dg[k]] + rank[k];
-      S.stage[pos] = e[k];
-      S.sdig[pos] = (unsigned short)dg[k];
+      S.slot[pos] = (dg[k] << 16) | (u32)(warp * (32 * kSortItems) + k * 32 + lane);
     }
   }
 
   // ---- decoupled look-back for digit `tid`
   if (tid < kRadixBins) {
     u32 prefix = 0;
-    if (tile > 0) {
+    if (tile > 0 && live_digit) {
       // walk back over the predecessors' words, kLookBatch independent loads per round trip
       constexpr int kLookBatch = 8;
       bool done = false;
@@ -316,17 +386,15 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   }
   __syncthreads();
 
-  // ---- 4. copy out: consecutive threads write consecutive addresses inside a digit run
+  // ---- 4. copy out through the permutation
   const int n_valid_tile = (int)S.n_valid_tile;
   for (int i = tid; i < n_valid_tile; i += kSortThreads) {
-    const u32 d = S.sdig[i];
-    st_stream(dst + S.gbase[d] + i, S.stage[i]);
+    const u32 s = S.slot[i];
+    const u32 from = s & 0xFFFFu;
+    float4 e = S.in[from];
+    if (FIRST) e.w = __uint_as_float(P.idx_offset + (u32)(start + base + from));
+    st_stream(dst + S.gbase[s >> 16] + i, e);
   }
-  if (FIRST)
-    for (int i = tid; i < (n_passes - 1) * kRadixBins; i += kSortThreads) {
-      const u32 c = (&S.later_hist[0][0])[i];
-      if (c) atomicAdd(&hist_all[kRadixBins + i], c);
-    }
 }
 
 }  // namespace gndt

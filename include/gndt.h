@@ -243,6 +243,12 @@ void gndt_morton_to_xy(uint32_t morton, uint32_t *nx, uint32_t *ny);
 /* The reference's string key: quadrant letter + decimal Morton, e.g. "A55".
  * buf must hold >= 16 chars.  Returns the string length. */
 int gndt_morton_string(int32_t sx, int32_t sy, char *buf);
+/* TwoDmap::countPositionXYZ (include/map2D.h:918-947): centre of cell (sx,sy,sz), metres. */
+int gndt_cell_center(const float origin[3], float grid_len, float z_len, int32_t sx, int32_t sy,
+                     int32_t sz, float center[3]);
+/* The map origin in use (TwoDmap::cloudFirst, map2D.h:193,490-492): point 0 of the initial
+ * cloud when origin_is_first_point, else params.origin. */
+int gndt_origin(gndt_handle *h, float origin[3]);
 
 #ifdef __cplusplus
 }
