@@ -1,0 +1,105 @@
+// gndt_twodmap_adapter.h — header-only bridge from the libgndt.so result tables to the
+// reference's own containers, so that its host-side planner (TwoDmap::computeCost,
+// AstarPlanar in GlobalPlan.h, the show* marker builders) keeps running unmodified.
+//
+// Include AFTER the reference's "map2D.h" (it uses daysun::TwoDmap / Cell / Slope / OcNode
+// and the reference's countMorton).  Not part of the C ABI; plain C++98-compatible code.
+//
+// What it rebuilds, and where the reference builds the same thing:
+//   morton_list                 xy keys in first-seen order              src/receiver.cpp:70
+//   map_cell / Cell::map_slope  one Cell per occupied column, one Slope  include/map2D.h:598-599,
+//                               per surface voxel                        632-642 / 646-659
+//   map_xy                      OcNode{z, morton, xyz_centroid,          src/receiver.cpp:62-69,85-90;
+//                               covariance_matrix, N} in first-seen      include/map2D.h:623-625
+//                               order inside each column
+#ifndef GNDT_TWODMAP_ADAPTER_H
+#define GNDT_TWODMAP_ADAPTER_H
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../include/gndt.h"
+
+namespace gndt_adapter {
+
+// "A"+countMorton(|sx|,|sy|) — the reference's own key builder (map2D.h:971-972)
+inline std::string morton_key(int sx, int sy) {
+  const char q = sx > 0 ? (sy > 0 ? 'A' : 'B') : (sy > 0 ? 'C' : 'D');
+  return std::string(1, q) + countMorton(std::abs(sx), std::abs(sy));
+}
+
+struct ByFirst {
+  const gndt_voxel *v;
+  explicit ByFirst(const gndt_voxel *vv) : v(vv) {}
+  bool operator()(unsigned a, unsigned b) const { return v[a].first_index < v[b].first_index; }
+};
+struct ColByFirst {
+  const gndt_column *c;
+  explicit ColByFirst(const gndt_column *cc) : c(cc) {}
+  bool operator()(unsigned a, unsigned b) const { return c[a].first_index < c[b].first_index; }
+};
+
+// Fill `m` (freshly constructed, parameters already set with setLen/setZLen/setInterval)
+// from the tables of one build.  `with_map_xy` also recreates the OcNode multimap (needed
+// by Slope::countUp in the "true" demand and by showInital); the slope demand's planner
+// only reads map_cell.
+inline void fill_twodmap(daysun::TwoDmap &m, const float origin[3], const gndt_voxel *vox, size_t n_vox,
+                         const gndt_slope *slopes, size_t n_slopes, const gndt_column *cols, size_t n_cols,
+                         bool with_map_xy) {
+  (void)n_vox;
+  m.setCloudFirst(octomath::Vector3(origin[0], origin[1], origin[2]));
+  std::vector<unsigned> order(n_cols);
+  for (size_t c = 0; c < n_cols; ++c) order[c] = (unsigned)c;
+  std::sort(order.begin(), order.end(), ColByFirst(cols));
+  for (size_t k = 0; k < n_cols; ++k) {
+    const gndt_column &col = cols[order[k]];
+    const std::string key = morton_key(col.sx, col.sy);
+    m.morton_list.push_back(key);
+    daysun::Cell *cell = new daysun::Cell(key);
+    m.map_cell.insert(std::map<std::string, daysun::Cell *>::value_type(key, cell));
+    for (unsigned s = col.slope_begin; s < col.slope_begin + col.slope_count && s < n_slopes; ++s) {
+      const gndt_slope &g = slopes[s];
+      daysun::Slope *slope = new daysun::Slope();
+      slope->morton_xy = key;
+      slope->morton_z = g.sz;
+      slope->normal << g.normal[0], g.normal[1], g.normal[2];
+      slope->rough = g.rough;
+      slope->mean(0) = g.mean[0]; slope->mean(1) = g.mean[1]; slope->mean(2) = g.mean[2];
+      slope->h = slope->g = slope->f = FLT_MAX;
+      // slope demand: never assigned on the initial build (map2D.h:636) and a Slope never
+      // carries UP there; true demand: what the lazy Slope::countUp (map2D.h:275) would store
+      slope->up = (g.flags & GNDT_F_UP) != 0;
+      slope->down = (g.flags & GNDT_F_DOWN) != 0;
+      slope->father = NULL;
+      cell->map_slope.insert(std::make_pair(g.sz, slope));
+    }
+    if (with_map_xy) {
+      std::vector<unsigned> vs(col.voxel_count);
+      for (unsigned i = 0; i < col.voxel_count; ++i) vs[i] = col.voxel_begin + i;
+      std::sort(vs.begin(), vs.end(), ByFirst(vox));  // multimap equal-range order = first seen
+      for (size_t i = 0; i < vs.size(); ++i) {
+        const gndt_voxel &v = vox[vs[i]];
+        daysun::OcNode *node = new daysun::OcNode();
+        node->morton = key;
+        node->z = v.sz;
+        if (v.flags & GNDT_F_FITTED) {
+          node->N = (int)v.count;
+          node->xyz_centroid << v.mean[0], v.mean[1], v.mean[2];
+          node->covariance_matrix(0, 0) = v.scatter[0]; node->covariance_matrix(0, 1) = v.scatter[1];
+          node->covariance_matrix(0, 2) = v.scatter[2]; node->covariance_matrix(1, 1) = v.scatter[3];
+          node->covariance_matrix(1, 2) = v.scatter[4]; node->covariance_matrix(2, 2) = v.scatter[5];
+          node->covariance_matrix(1, 0) = v.scatter[1]; node->covariance_matrix(2, 0) = v.scatter[2];
+          node->covariance_matrix(2, 1) = v.scatter[4];
+          node->_isSlope = (v.flags & GNDT_F_SLOPE) != 0;
+        }
+        m.map_xy.insert(std::multimap<std::string, daysun::OcNode *>::value_type(key, node));
+      }
+    }
+  }
+}
+
+}  // namespace gndt_adapter
+#endif

@@ -59,7 +59,9 @@ class Slope:
         self.morton_xy = key
         self.morton_z = int(rec["sz"])
         self.flags = int(rec["flags"])
-        self.up = False  # never assigned on the initial build (map2D.h:636)
+        # slope demand: never assigned (map2D.h:636) and never set on a Slope; true demand: the
+        # value the lazy Slope::countUp would store (map2D.h:275)
+        self.up = bool(self.flags & _abi.F_UP)
         self.down = bool(self.flags & _abi.F_DOWN)
         self.father = None
 

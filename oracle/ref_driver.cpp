@@ -238,3 +238,4 @@ int gndt_ref_trans_morton_xyz(const float origin[3], float grid_len, float z_len
 }
 
 }  // extern "C"
+#include "ref_adapter_check.cpp"
