@@ -226,7 +226,9 @@ def main():
     counts = m.counts()
     stages = m.stage_ms()
 
-    # ---- end to end: pinned host cloud in, tables out, every step
+    # ---- end to end: pinned host cloud in, tables out (into pinned host buffers), every step
+    m.pin_results(True)
+
     def e2e_step():
         step(host)
         v, s, c = m.voxels, m.slopes, m.columns

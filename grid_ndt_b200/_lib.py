@@ -60,6 +60,7 @@ SYMBOLS = {
     "gndt_plan_tiles": (_i, [_vp, _vp, _sz, _sz, _i, _i, C.POINTER(C.c_int32), _vp]),
     "gndt_stage_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "gndt_launch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "gndt_fast_div_status": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "gndt_trans_morton_xyz": (_i, [C.POINTER(C.c_float), C.c_float, C.c_float, C.POINTER(C.c_float),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gndt_count_morton": (C.c_uint32, [C.c_uint32, C.c_uint32]),

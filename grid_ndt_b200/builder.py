@@ -173,9 +173,26 @@ class TwoDmap:
         _check(self._h, lib().gndt_counts(self._h, C.byref(c)))
         return c.as_dict()
 
+    def _result_buffer(self, name, dtype, n):
+        """Host destination for a result table.  With pinned_results the buffers are
+        page-locked (and reused across builds), so the device->host copy runs at PCIe speed."""
+        if not getattr(self, "_pinned", False) or torch is None:
+            return np.zeros(max(n, 1), dtype)
+        need = max(n, 1) * dtype.itemsize
+        buf = self._pinned_bufs.get(name)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+            self._pinned_bufs[name] = buf
+        return buf.numpy()[:need].view(dtype)
+
+    def pin_results(self, on: bool = True):
+        self._pinned = bool(on)
+        self._pinned_bufs = getattr(self, "_pinned_bufs", {})
+        return self
+
     def _table(self, name, fn, dtype, n):
         if name not in self._tables:
-            out = np.zeros(max(n, 1), dtype)
+            out = self._result_buffer(name, dtype, n)
             got = C.c_size_t()
             _check(self._h, fn(self._h, out.ctypes.data, n, _abi.GNDT_MEM_HOST, C.byref(got)))
             self._tables[name] = out[: got.value]
@@ -214,6 +231,13 @@ class TwoDmap:
         ms = (C.c_float * _abi.N_STAGES)()
         _check(self._h, lib().gndt_stage_ms(self._h, ms))
         return {k: float(ms[i]) for i, k in enumerate(_abi.STAGE_NAMES) if k != "reserved"}
+
+    def fast_div_status(self):
+        """(enabled, values_checked): whether the hoisted index division passed its exhaustive
+        on-device equality check against the IEEE division for this map's cell lengths."""
+        en, n = C.c_int(), C.c_uint64()
+        _check(self._h, lib().gndt_fast_div_status(self._h, C.byref(en), C.byref(n)))
+        return bool(en.value), int(n.value)
 
     def launch_count(self) -> int:
         n = C.c_uint64()

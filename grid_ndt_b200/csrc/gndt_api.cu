@@ -30,6 +30,12 @@ struct Buffer {
 
 enum EvId { EV_H2D0, EV_START, EV_KEY, EV_SORT, EV_REDUCE, EV_LABEL, EV_EDGES, EV_COUNT };
 
+struct DivCheck {  // result of the exhaustive hoisted-division check for one cell length
+  float len = -1.f;
+  float rinv = 0.f;
+  int ok = 0;
+};
+
 }  // namespace
 
 struct gndt_handle {
@@ -67,6 +73,8 @@ struct gndt_handle {
   uint64_t launches = 0;
   uint64_t total_points = 0;  // points handed to build + updates so far (host copy)
   int sm_count = 148;
+  DivCheck div[2];            // [0] grid_len, [1] z_len
+  uint64_t divcheck_values = 0;
 };
 
 namespace {
@@ -130,6 +138,8 @@ DevParams to_dev(const gndt_params &p, size_t cap_voxels) {
   d.max_abs[0] = max_abs_offset(p.grid_len);
   d.max_abs[1] = max_abs_offset(p.z_len);
   d.idx_offset = 0;
+  d.fast_div = 0;
+  d.rinv[0] = d.rinv[1] = 0.f;
   d.grid_len = p.grid_len; d.z_len = p.z_len; d.slope_interval = p.slope_interval;
   d.demand = p.demand; d.min_points = p.min_points;
   d.rough_max = p.rough_max; d.angle_max_deg = p.angle_max_deg; d.reach_height = p.reach_height;
@@ -138,6 +148,55 @@ DevParams to_dev(const gndt_params &p, size_t cap_voxels) {
   d.normalize_cov = p.normalize_cov;
   d.tile_lo = p.tile_lo; d.tile_hi = p.tile_hi;
   d.max_voxels = (u32)cap_voxels;
+  return d;
+}
+
+// Exhaustive proof-by-enumeration that the hoisted division (gndt_device.cuh) rounds exactly
+// like the IEEE division for this cell length: every float a in [len, 2*max_abs] is tried.
+// (a < len never divides; beyond 2*max_abs both quotients exceed GNDT_MAX_INDEX by far.)
+__global__ void divcheck_kernel(float len, u32 lo_bits, u32 hi_bits, float *rinv_out, unsigned long long *mismatches) {
+  const float r = refined_rcp(len);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *rinv_out = r;
+  unsigned long long bad = 0;
+  for (u64 b = (u64)lo_bits + (u64)blockIdx.x * blockDim.x + threadIdx.x; b <= hi_bits; b += (u64)gridDim.x * blockDim.x) {
+    const float a = __uint_as_float((u32)b);
+    const float exact = ceilf(__fdiv_rn(a, len));
+    const float fast = hoisted_div_ceil(a, len, r);
+    if (!(exact == fast)) bad++;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+int verify_fast_div(gndt_handle *h, float len, DivCheck &out) {
+  if (out.len == len) return GNDT_OK;  // cached for this length
+  out.len = len;
+  out.ok = 0;
+  out.rinv = 0.f;
+  const char *force = getenv("GNDT_EXACT_DIV");
+  if (force && force[0] == '1') return GNDT_OK;
+  void *scratch = nullptr;
+  GNDT_CUDA(h, cudaMalloc(&scratch, 64));
+  GNDT_CUDA(h, cudaMemset(scratch, 0, 64));
+  uint32_t lo, hi;
+  const float top = 2.f * max_abs_offset(len);
+  memcpy(&lo, &len, 4);
+  memcpy(&hi, &top, 4);
+  divcheck_kernel<<<h->sm_count * 8, 256>>>(len, lo, hi, (float *)scratch, (unsigned long long *)((char *)scratch + 8));
+  unsigned long long host[2] = {0, 0};
+  cudaError_t e = cudaMemcpy(host, scratch, 16, cudaMemcpyDeviceToHost);
+  cudaFree(scratch);
+  if (e != cudaSuccess) { h->err = std::string("divcheck: ") + cudaGetErrorString(e); return GNDT_ERR_CUDA; }
+  memcpy(&out.rinv, &host[0], 4);
+  out.ok = (host[1] == 0) ? 1 : 0;
+  h->divcheck_values += (uint64_t)hi - lo + 1;
+  return GNDT_OK;
+}
+
+DevParams make_dev(gndt_handle *h, const gndt_params &p, size_t cap_voxels) {
+  DevParams d = to_dev(p, cap_voxels);
+  d.fast_div = (h->div[0].ok && h->div[1].ok && h->div[0].len == p.grid_len && h->div[1].len == p.z_len) ? 1 : 0;
+  d.rinv[0] = h->div[0].rinv;
+  d.rinv[1] = h->div[1].rinv;
   return d;
 }
 
@@ -320,6 +379,9 @@ int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
   if (e != cudaSuccess) { g_create_error = std::string("kernel image for sm_100a not loadable on this device: ") + cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
+  int rc = verify_fast_div(h, h->params.grid_len, h->div[0]);
+  if (rc == GNDT_OK) rc = verify_fast_div(h, h->params.z_len, h->div[1]);
+  if (rc != GNDT_OK) { g_create_error = h->err; delete h; return rc; }
   *out = h;
   return GNDT_OK;
 }
@@ -339,7 +401,10 @@ int gndt_destroy(gndt_handle *h) {
 int gndt_set_params(gndt_handle *h, const gndt_params *params) {
   if (!h || validate_params(params) != GNDT_OK) return GNDT_ERR_INVALID_ARG;
   h->params = *params;
-  return GNDT_OK;
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  int rc = verify_fast_div(h, h->params.grid_len, h->div[0]);  // no-op when the length is unchanged
+  if (rc == GNDT_OK) rc = verify_fast_div(h, h->params.z_len, h->div[1]);
+  return rc;
 }
 
 int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
@@ -364,7 +429,7 @@ int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, i
     h->timed_h2d = true;
   }
   const size_t start = h->params.origin_is_first_point ? 1 : 0;
-  const DevParams dp = to_dev(h->params, h->cap_voxels);
+  const DevParams dp = make_dev(h, h->params, h->cap_voxels);
 
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
   rc = front_end(h, st, d_in, n, stride_bytes / 4, start, dp, (VoxMoments *)h->mom.p);
@@ -419,7 +484,7 @@ int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, 
   gndt_params p = h->params;  // every point of the scan is binned against the resident origin
   p.origin_is_first_point = 0;
   p.origin[0] = origin[0]; p.origin[1] = origin[1]; p.origin[2] = origin[2];
-  DevParams dp = to_dev(p, cap_vox);
+  DevParams dp = make_dev(h, p, cap_vox);
   dp.idx_offset = (u32)h->total_points;
 
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
@@ -516,7 +581,7 @@ int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t b
   Ctl *ctl = reinterpret_cast<Ctl *>(z);
   u32 *rs = reinterpret_cast<u32 *>(z + o_rs), *re = reinterpret_cast<u32 *>(z + o_re);
   u64 *bs = reinterpret_cast<u64 *>(z + o_bs);
-  const DevParams dp = to_dev(h->params, n_table);
+  const DevParams dp = make_dev(h, h->params, n_table);
   const int g = grid_for(h, n_table, kLabelThreads, 8);
   table_bounds_kernel<<<1, 32, 0, st>>>(ctl, table, (u32)n_table);
   label_kernel<<<g, kLabelThreads, 0, st>>>(ctl, table, (u32)n_table, (gndt_slope *)h->f_slopes.p,
@@ -537,7 +602,7 @@ __global__ void cx_hist_kernel(u32 *hist, const float *in, size_t stride_f, size
   for (size_t i = start + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += (size_t)gridDim.x * blockDim.x) {
     float4 p = load_point(in, stride_f, i, vec);
     int cx, cy, cz;
-    if (point_indices(p.x, p.y, p.z, o, P.grid_len, P.z_len, cx, cy, cz)) atomicAdd(&hist[cx + kIdxBias], 1u);
+    if (point_indices(p.x, p.y, p.z, o, P, cx, cy, cz)) atomicAdd(&hist[cx + kIdxBias], 1u);
   }
 }
 
@@ -555,7 +620,7 @@ int gndt_plan_tiles(gndt_handle *h, const void *xyz, size_t n, size_t stride_byt
   }
   if ((rc = ensure(h, h->f_zero, 65536 * sizeof(u32) + 1024)) != GNDT_OK) return rc;
   GNDT_CUDA(h, cudaMemsetAsync(h->f_zero.p, 0, 65536 * sizeof(u32), st));
-  const DevParams dp = to_dev(h->params, 0);
+  const DevParams dp = make_dev(h, h->params, 0);
   cx_hist_kernel<<<grid_for(h, n, 256 * 8, 8), 256, 0, st>>>((u32 *)h->f_zero.p, d_in, stride_bytes / 4, n,
                                                              h->params.origin_is_first_point ? 1 : 0, dp);
   h->launches += 1;
@@ -590,6 +655,13 @@ int gndt_stage_ms(gndt_handle *h, float ms[GNDT_N_STAGES]) {
   GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_EDGES], h->ev[EV_LABEL], h->ev[EV_EDGES]));
   GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_TOTAL], h->ev[EV_START], h->ev[EV_EDGES]));
   if (h->timed_h2d) GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_H2D], h->ev[EV_H2D0], h->ev[EV_START]));
+  return GNDT_OK;
+}
+
+int gndt_fast_div_status(gndt_handle *h, int *enabled, uint64_t *values_checked) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  if (enabled) *enabled = (h->div[0].ok && h->div[1].ok) ? 1 : 0;
+  if (values_checked) *values_checked = h->divcheck_values;
   return GNDT_OK;
 }
 

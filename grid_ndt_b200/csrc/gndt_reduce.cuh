@@ -167,7 +167,7 @@ struct RedSmem {
 
 __device__ __forceinline__ u64 point_key(const float4 &p, const float o[3], const DevParams &P) {
   int cx, cy, cz;
-  point_indices(p.x, p.y, p.z, o, P.grid_len, P.z_len, cx, cy, cz);
+  point_indices(p.x, p.y, p.z, o, P, cx, cy, cz);
   return voxel_key(cx, cy, cz);
 }
 

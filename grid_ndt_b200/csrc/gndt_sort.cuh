@@ -102,24 +102,42 @@ __global__ void __launch_bounds__(256) bounds_kernel(Ctl *ctl, u32 *hist0, const
   const float inf = __int_as_float(0x7f800000);
   float lo_x = inf, lo_y = inf, lo_z = inf, hi_x = -inf, hi_y = -inf, hi_z = -inf;
   u32 n_ok = 0, n_drop = 0, n_out = 0;
-  for (size_t i = start + (size_t)blockIdx.x * blockDim.x + tid; i < n_in; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 p = load_point(in, stride_f, i, vec);
-    const bool ok = fabsf(__fsub_rn(p.x, o[0])) <= P.max_abs[0] && fabsf(__fsub_rn(p.y, o[1])) <= P.max_abs[0] &&
-                    fabsf(__fsub_rn(p.z, o[2])) <= P.max_abs[1];
-    if (!ok) { n_drop++; continue; }  // NaN / Inf / out of the supported index range
-    if (tiled) {
-      int cx;
-      axis_index(p.x, o[0], P.grid_len, cx);
-      if (cx < P.tile_lo || cx >= P.tile_hi) { n_out++; continue; }
+  // 4 points per thread per trip: the loads are issued together, all lanes stay converged
+  // (no early `continue`) so the warp-aggregated histogram update sees full warps
+  constexpr int kUnroll = 4;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t w0 = start + (size_t)blockIdx.x * blockDim.x + (tid & ~31); w0 < n_in; w0 += kUnroll * step) {  // warp-uniform trip count
+    const size_t i0 = w0 + lane;
+    float4 p[kUnroll];
+#pragma unroll
+    for (int u2 = 0; u2 < kUnroll; ++u2) {
+      const size_t i = i0 + u2 * step;
+      p[u2] = (i < n_in) ? load_point(in, stride_f, i, vec) : make_float4(inf, inf, inf, 0.f);
     }
-    n_ok++;
-    lo_x = fminf(lo_x, p.x); lo_y = fminf(lo_y, p.y); lo_z = fminf(lo_z, p.z);
-    hi_x = fmaxf(hi_x, p.x); hi_y = fmaxf(hi_y, p.y); hi_z = fmaxf(hi_z, p.z);
-    int cz;
-    axis_index(p.z, o[2], P.z_len, cz);
-    const u32 d = first_digit(cz);
-    const u32 peers = __match_any_sync(__activemask(), d);  // flat scenes: most lanes share a z bin
-    if (lane == __ffs(peers) - 1) atomicAdd(&sh[d], (u32)__popc(peers));
+#pragma unroll
+    for (int u2 = 0; u2 < kUnroll; ++u2) {
+      const size_t i = i0 + u2 * step;
+      const bool live = i < n_in;
+      bool ok = live && fabsf(__fsub_rn(p[u2].x, o[0])) <= P.max_abs[0] && fabsf(__fsub_rn(p[u2].y, o[1])) <= P.max_abs[0] &&
+                fabsf(__fsub_rn(p[u2].z, o[2])) <= P.max_abs[1];
+      if (live && !ok) n_drop++;  // NaN / Inf / out of the supported index range
+      if (ok && tiled) {
+        int cx;
+        axis_idx(p[u2].x, o[0], false, P, cx);
+        if (cx < P.tile_lo || cx >= P.tile_hi) { n_out++; ok = false; }
+      }
+      u32 d = kInvalidDigit;
+      if (ok) {
+        n_ok++;
+        lo_x = fminf(lo_x, p[u2].x); lo_y = fminf(lo_y, p[u2].y); lo_z = fminf(lo_z, p[u2].z);
+        hi_x = fmaxf(hi_x, p[u2].x); hi_y = fmaxf(hi_y, p[u2].y); hi_z = fmaxf(hi_z, p[u2].z);
+        int cz;
+        axis_idx(p[u2].z, o[2], true, P, cz);
+        d = first_digit(cz);
+      }
+      const u32 peers = __match_any_sync(0xffffffffu, d);  // flat scenes: most lanes share a z bin
+      if (ok && lane == __ffs(peers) - 1) atomicAdd(&sh[d], (u32)__popc(peers));
+    }
   }
 #pragma unroll
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(Ctl *ctl, u32 *hist0, const
     for (int w = 1; w < 8; ++w) m = (tid < 3) ? fmaxf(m, red[tid][w]) : fminf(m, red[tid][w]);
     const int ax = tid % 3;
     int c;
-    axis_index(m, o[ax], ax == 2 ? P.z_len : P.grid_len, c);  // index of the extreme coordinate
+    axis_idx(m, o[ax], ax == 2, P, c);  // index of the extreme coordinate
     atomicMax(&ctl->max_cx_b + tid, (u32)((tid < 3 ? c : -c) + kIdxBias));
   }
   if (tid == 0) {
@@ -279,7 +297,7 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
       const float4 e = S.in[i];
       int cx, cy, cz;
       if (FIRST) {
-        bool ok = point_indices(e.x, e.y, e.z, o, P.grid_len, P.z_len, cx, cy, cz);
+        bool ok = point_indices(e.x, e.y, e.z, o, P, cx, cy, cz);
         if (ok && tiled && (cx < P.tile_lo || cx >= P.tile_hi)) ok = false;
         if (ok) {
           dg[k] = first_digit(cz);
@@ -289,7 +307,7 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
             if (q < n_passes) atomicAdd(&later_hist[(q - 1) * kRadixBins + ((u32)(key >> q_shift[q]) & q_mask[q])], 1u);
         }
       } else {
-        point_indices_masked(e.x, e.y, e.z, o, P.grid_len, P.z_len, need, cx, cy, cz);
+        point_indices_masked(e.x, e.y, e.z, o, P, need, cx, cy, cz);
         u32 d = 0;
         if (need & 1) d |= ((u32)(cx - L.cx_min) >> rs_x) << ls_x;
         if (need & 2) d |= ((u32)(cy - L.cy_min) >> rs_y) << ls_y;
@@ -360,7 +378,10 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
   if (tid < kRadixBins) {
     u32 prefix = 0;
     if (tile > 0 && live_digit) {
-      // walk back over the predecessors' words, kLookBatch independent loads per round trip
+      // Walk back over the predecessors' words, 8 independent loads per round trip.  Measured
+      // (clock64 per phase): this wait is 22-37 % of a CTA's life; 32 per trip and an early
+      // prefetch were both SLOWER - the walk is bounded by the L2 traffic of 256 digit threads
+      // x ~70 in-flight tiles, not by its latency.  See DESIGN.md §3 for the planned fix.
       constexpr int kLookBatch = 8;
       bool done = false;
       for (int j = tile - 1; j >= 0 && !done; j -= kLookBatch) {

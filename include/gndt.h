@@ -228,6 +228,12 @@ int gndt_plan_tiles(gndt_handle *h, const void *xyz, size_t n, size_t stride_byt
 int gndt_stage_ms(gndt_handle *h, float ms[GNDT_N_STAGES]);
 /* number of kernel launches issued by the last build/update on this handle */
 int gndt_launch_count(gndt_handle *h, uint64_t *n_launches);
+/* The cell index needs one IEEE binary32 division per axis (map2D.h:965-967).  For the cell
+ * lengths of this handle the library verifies on the device, for EVERY float in range, that
+ * a division with the reciprocal refinement hoisted out rounds identically; *enabled says
+ * whether that check passed (else the plain division is used), *values_checked how many
+ * operands were compared.  GNDT_EXACT_DIV=1 in the environment forces the plain division. */
+int gndt_fast_div_status(gndt_handle *h, int *enabled, uint64_t *values_checked);
 
 /* ---- host-side key helpers (pure C, no device) ------------------------------------- */
 

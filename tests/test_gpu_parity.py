@@ -254,3 +254,28 @@ def test_world2_strips_nccl():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29611", os.path.join(root, "tests", "multi_gpu_worker.py")], capture_output=True, timeout=600)
     assert out.returncode == 0, out.stdout.decode()[-3000:] + out.stderr.decode()[-3000:]
+
+
+def test_hoisted_division_is_verified_and_equivalent():
+    """The hoisted index division must have passed its exhaustive on-device check for the
+    lengths in use, and a build with the plain IEEE division (GNDT_EXACT_DIV=1, separate
+    process) must produce byte-identical tables."""
+    _gpu()
+    import subprocess, sys, hashlib
+    cloud = synthetic.cfg2(300_000, scale=0.2)
+    m = _build(cloud, 0.2, 0.1)
+    enabled, checked = m.fast_div_status()
+    assert enabled and checked > 100_000_000, (enabled, checked)
+    digest = hashlib.sha256(m.voxels.tobytes() + m.slopes.tobytes() + m.columns.tobytes()).hexdigest()
+    m.close()
+    code = ("import hashlib; from grid_ndt_b200 import TwoDmap, synthetic; c = synthetic.cfg2(300_000, scale=0.2); "
+            "m = TwoDmap(0.2, 0.1); m.setInterval(0.08); m.chatterCallback(c, 'slope'); assert not m.fast_div_status()[0]; "
+            "print(hashlib.sha256(m.voxels.tobytes() + m.slopes.tobytes() + m.columns.tobytes()).hexdigest())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, cwd=root, env=dict(os.environ, GNDT_EXACT_DIV="1"), timeout=300)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    assert out.stdout.decode().strip().splitlines()[-1] == digest
+    for gl, zl in ((0.05, 0.05), (0.1, 0.05), (0.25, 0.1), (0.5, 0.1), (1.0, 0.1), (0.3, 0.07)):
+        mm = _build(synthetic.cfg1(20_000), gl, zl)
+        assert mm.fast_div_status()[0], (gl, zl)
+        mm.close()
