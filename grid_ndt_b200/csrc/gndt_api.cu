@@ -45,7 +45,7 @@ struct gndt_handle {
   // workspace sized by points
   Buffer in_stage, buf_a, buf_b, zero;
   // workspace sized by voxels
-  Buffer mom, mom_alt, table, slopes, columns;
+  Buffer mom, mom_alt, table, slopes, columns, vfirst;
   // streaming update scratch (sized by the scan)
   Buffer mom_scan, upd_flags, upd_pos, upd_keys;
   Buffer small;  // Totals + n_new word, never memset by a build
@@ -221,6 +221,7 @@ int reserve(gndt_handle *h, size_t n, size_t cap_vox, bool host_input, size_t st
   if ((rc = ensure(h, h->table, cap_vox * sizeof(gndt_voxel))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->slopes, cap_vox * sizeof(gndt_slope))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->columns, cap_vox * sizeof(gndt_column))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->vfirst, cap_vox * sizeof(u32))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->small, 256)) != GNDT_OK) return rc;
   h->cap_points = n;
   h->cap_voxels = cap_vox;
@@ -313,19 +314,20 @@ __global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_fix
 // sorted raw moments -> voxel / slope / column tables + reachability bits
 int back_end(gndt_handle *h, cudaStream_t st, const DevParams &dp, const VoxMoments *mom, bool bounds_from_table) {
   const int g_lab = grid_for(h, h->cap_voxels, kLabelThreads, 8);
-  finalize_label_kernel<<<g_lab, kLabelThreads, 0, st>>>(h->ctl, mom, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
-                                                         (gndt_column *)h->columns.p, h->blk_state, &h->ctl->ticket[7], dp);
+  finalize_label_kernel<<<g_lab, kLabelThreads, sizeof(FinSmem), st>>>(h->ctl, mom, (gndt_voxel *)h->table.p,
+                                                                       (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p,
+                                                                       (u32 *)h->vfirst.p, h->blk_state, &h->ctl->ticket[7], dp);
   if (bounds_from_table) {
     table_bounds_kernel<<<1, 32, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, 0u);
     h->launches += 1;
   }
-  column_finish_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, 0u, (gndt_column *)h->columns.p,
-                                              h->row_start, h->row_end, 0, 0);
+  column_finish_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const u32 *)h->vfirst.p, 0u,
+                                              (gndt_column *)h->columns.p, h->row_start, h->row_end, 0, 0);
   h->launches += 2;
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_LABEL], st));
   edges_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
                                       (const gndt_column *)h->columns.p, h->row_start, h->row_end, 0, 0, 0, 0u,
-                                      0xFFFFFFFFu, dp);
+                                      0xFFFFFFFFu, nullptr, 0, dp);
   h->launches += 1;
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_EDGES], st));
   return GNDT_OK;
@@ -378,6 +380,7 @@ int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
   e = cudaFuncSetAttribute(sort_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(finalize_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem));
   if (e != cudaSuccess) { g_create_error = std::string("kernel image for sm_100a not loadable on this device: ") + cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
   int rc = verify_fast_div(h, h->params.grid_len, h->div[0]);
   if (rc == GNDT_OK) rc = verify_fast_div(h, h->params.z_len, h->div[1]);
@@ -390,7 +393,7 @@ int gndt_destroy(gndt_handle *h) {
   if (!h) return GNDT_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
-                    &h->columns, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small,
+                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small,
                     &h->f_slopes, &h->f_columns, &h->f_zero};
   for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
   for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -564,33 +567,79 @@ int gndt_device_voxels(gndt_handle *h, const gndt_voxel **dptr, size_t *n) {
   return GNDT_OK;
 }
 
-int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin, size_t count, void *stream) {
-  if (!h || (!table && n_table) || begin + count > n_table || n_table > 0xFFFFFFFEull) return GNDT_ERR_INVALID_ARG;
+// x rows that sit on a strip boundary of an all-gathered table: first and last row of every strip
+__global__ void halo_rows_kernel(const gndt_voxel *table, const u64 *offsets, int n_strips, int *rows) {
+  const int r = threadIdx.x;
+  if (r >= n_strips) return;
+  const u64 lo = offsets[r], hi = offsets[r + 1];
+  const int none = 0x7fffffff;
+  rows[2 * r] = (hi > lo) ? contiguous_index(table[lo].sx) : none;
+  rows[2 * r + 1] = (hi > lo) ? contiguous_index(table[hi - 1].sx) : none;
+}
+
+static int label_edges_impl(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin, size_t count,
+                            const uint64_t *offsets, int n_strips, cudaStream_t st) {
+  if (!h || (!table && n_table) || begin + count > n_table || n_table > 0xFFFFFFFEull || n_strips > 64) return GNDT_ERR_INVALID_ARG;
   if (n_table == 0) return GNDT_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   GNDT_CUDA(h, cudaSetDevice(h->device));
   int rc;
   if ((rc = ensure(h, h->f_slopes, n_table * sizeof(gndt_slope))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->f_columns, n_table * sizeof(gndt_column))) != GNDT_OK) return rc;
   const size_t blocks = (n_table + kLabelThreads - 1) / kLabelThreads;
-  const size_t o_rs = align_up(sizeof(Ctl), 256), o_re = o_rs + 65536 * 4, o_bs = o_re + 65536 * 4;
+  const size_t o_rs = align_up(sizeof(Ctl), 256), o_re = o_rs + 65536 * 4, o_hr = o_re + 65536 * 4, o_of = o_hr + 1024,
+               o_bs = o_of + 1024;
   const size_t zbytes = o_bs + blocks * sizeof(u64);
   if ((rc = ensure(h, h->f_zero, zbytes)) != GNDT_OK) return rc;
   GNDT_CUDA(h, cudaMemsetAsync(h->f_zero.p, 0, zbytes, st));
   char *z = static_cast<char *>(h->f_zero.p);
   Ctl *ctl = reinterpret_cast<Ctl *>(z);
   u32 *rs = reinterpret_cast<u32 *>(z + o_rs), *re = reinterpret_cast<u32 *>(z + o_re);
+  int *halo_rows = reinterpret_cast<int *>(z + o_hr);
+  u64 *d_off = reinterpret_cast<u64 *>(z + o_of);
   u64 *bs = reinterpret_cast<u64 *>(z + o_bs);
   const DevParams dp = make_dev(h, h->params, n_table);
   const int g = grid_for(h, n_table, kLabelThreads, 8);
+  int n_halo = 0;
+  if (offsets && n_strips > 1) {
+    GNDT_CUDA(h, cudaMemcpyAsync(d_off, offsets, (size_t)(n_strips + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+    halo_rows_kernel<<<1, 64, 0, st>>>(table, d_off, n_strips, halo_rows);
+    n_halo = 2 * n_strips;
+    h->launches += 1;
+  }
   table_bounds_kernel<<<1, 32, 0, st>>>(ctl, table, (u32)n_table);
   label_kernel<<<g, kLabelThreads, 0, st>>>(ctl, table, (u32)n_table, (gndt_slope *)h->f_slopes.p,
                                             (gndt_column *)h->f_columns.p, bs, &ctl->ticket[7], 0, dp);
-  column_finish_kernel<<<g, 256, 0, st>>>(ctl, table, (u32)n_table, (gndt_column *)h->f_columns.p, rs, re, 0, 0);
+  column_finish_kernel<<<g, 256, 0, st>>>(ctl, table, nullptr, (u32)n_table, (gndt_column *)h->f_columns.p, rs, re, 0, 0);
   edges_kernel<<<g, 256, 0, st>>>(ctl, table, (gndt_slope *)h->f_slopes.p, (const gndt_column *)h->f_columns.p, rs, re,
-                                  0, 0, 0, (u32)begin, (u32)(begin + count), dp);
+                                  0, 0, 0, (u32)begin, (u32)(begin + count), halo_rows, n_halo, dp);
   h->launches += 4;
   GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
+int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin, size_t count, void *stream) {
+  return label_edges_impl(h, table, n_table, begin, count, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int gndt_label_edges_strips(gndt_handle *h, gndt_voxel *table, const uint64_t *offsets, int n_strips, int my_strip,
+                            void *stream) {
+  if (!h || !offsets || n_strips < 1 || my_strip < 0 || my_strip >= n_strips) return GNDT_ERR_INVALID_ARG;
+  return label_edges_impl(h, table, (size_t)offsets[n_strips], (size_t)offsets[my_strip],
+                          (size_t)(offsets[my_strip + 1] - offsets[my_strip]), offsets, n_strips, static_cast<cudaStream_t>(stream));
+}
+
+int gndt_device_count_ptr(gndt_handle *h, const uint32_t **d_n_voxels) {
+  if (!h || !d_n_voxels) return GNDT_ERR_INVALID_ARG;
+  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
+  *d_n_voxels = &h->ctl->n_voxels;
+  return GNDT_OK;
+}
+
+int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capacity) {
+  if (!h || !dptr) return GNDT_ERR_INVALID_ARG;
+  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
+  *dptr = static_cast<const gndt_voxel *>(h->table.p);
+  if (capacity) *capacity = h->cap_voxels;
   return GNDT_OK;
 }
 

@@ -149,63 +149,119 @@ label_kernel(Ctl *ctl, gndt_voxel *table, u32 n_table_fixed, gndt_slope *slopes,
 //   * label it — the isSlope / countUp rules restated above, against the adjacent records
 //   * compact Slopes and Cells — CTA scan + decoupled look-back over (columns, slopes)
 // and write the 96-byte record exactly once.
+struct __align__(128) FinSmem {
+  VoxMoments in[kLabelThreads + 2];  // in[j] <-> voxel v0 - 1 + j (one halo record on each side)
+  float4 out[kLabelThreads * 6];     // the block's 256 finished 96-byte records
+  unsigned long long mbar;
+  u64 prefix;
+  u32 warp_sums[8];
+  u32 tile;
+};
+
 __global__ void __launch_bounds__(kLabelThreads, 3)
 finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_slope *slopes,
-                      gndt_column *columns, u64 *blk_state, u32 *counters, DevParams P) {
-  __shared__ u32 warp_sums[8];
-  __shared__ u32 s_tile;
-  __shared__ u64 s_prefix;
+                      gndt_column *columns, u32 *vfirst, u64 *blk_state, u32 *counters, DevParams P) {
+  extern __shared__ __align__(128) unsigned char smem_fin[];
+  FinSmem &S = *reinterpret_cast<FinSmem *>(smem_fin);
   const int tid = threadIdx.x;
   if (ctl->err) return;  // e.g. capacity exceeded: the moments table is incomplete
   const u32 V = ctl->n_voxels;
   const u32 n_blocks = (V + kLabelThreads - 1) / kLabelThreads;
-  for (;;) {
+  if (tid == 0) mbar_init(&S.mbar, 1);
+  for (u32 it = 0;; ++it) {
+    __syncthreads();  // everyone is done with in[] / out[] of the previous block
+    if (tid == 0) S.tile = atomicAdd(&counters[0], 1u);
     __syncthreads();
-    if (tid == 0) s_tile = atomicAdd(&counters[0], 1u);
-    __syncthreads();
-    const u32 blk = s_tile;
+    const u32 blk = S.tile;
     if (blk >= n_blocks) return;
-    const size_t v = (size_t)blk * kLabelThreads + tid;
-    const bool live = v < V;
-    float f[24];
-#pragma unroll
-    for (int i = 0; i < 24; ++i) f[i] = 0.f;
-    u32 *u = reinterpret_cast<u32 *>(f);
-    u32 flags = 0;
-    bool head = false;
+    const u32 v0 = blk * kLabelThreads;
+    const u32 cnt = min((u32)kLabelThreads, V - v0);
+    // one TMA bulk copy brings the block's moments plus one neighbour record on each side
+    if (tid == 0) {
+      const u32 lo = v0 > 0 ? v0 - 1 : 0, hi = min(v0 + cnt + 1, V);
+      tma_load_1d(&S.in[lo + 1 - v0], mom + lo, (hi - lo) * (u32)sizeof(VoxMoments), &S.mbar);
+    }
+    if (!mbar_wait(&S.mbar, it & 1)) atomicOr(&ctl->err, kErrWatchdog);
+    const u32 v = v0 + tid;
+    const bool live = tid < (int)cnt;
+
+    // ---- phase 1 (cheap): labels from the record headers, then the block's (columns,
+    // slopes) prefix.  Resolving the prefix BEFORE the expensive eigen work keeps the window
+    // in which successors see only an aggregate short, hence their look-back walks short.
+    u64 key = 0;
+    u32 count = 0, first = 0, flags = 0;
+    float mz = 0.f;
+    bool head = false, fitted = false;
     if (live) {
-      const VoxMoments me = mom[v];
-      const int cx = (int)(u32)(me.key >> 32) - kIdxBias, cy = (int)((u32)(me.key >> 16) & 0xFFFFu) - kIdxBias,
-                cz = (int)((u32)me.key & 0xFFFFu) - kIdxBias;
-      u[0] = (u32)signed_index(cx); u[1] = (u32)signed_index(cy); u[2] = (u32)signed_index(cz);
-      u[3] = me.count; u[4] = me.first;
-      const bool fitted = (int)me.count >= P.min_points;
-      const float mz = (float)me.m[2];
-      // vertical neighbours = adjacent records of the same column
-      bool has_lo = false, has_hi = false;
-      u64 lo_key = 0, hi_key = 0;
-      u32 lo_count = 0, lo_first = 0, hi_count = 0, hi_first = 0;
-      float lo_mz = 0.f, hi_mz = 0.f;
-      if (v > 0) {
-        const VoxMoments *q = mom + v - 1;
-        lo_key = q->key; lo_count = q->count; lo_first = q->first; lo_mz = (float)q->m[2];
-        has_lo = (lo_key >> 16) == (me.key >> 16);
-      }
-      if (v + 1 < V) {
-        const VoxMoments *q = mom + v + 1;
-        hi_key = q->key; hi_count = q->count; hi_first = q->first; hi_mz = (float)q->m[2];
-        has_hi = (hi_key >> 16) == (me.key >> 16);
-      }
+      const VoxMoments &me = S.in[tid + 1];
+      key = me.key; count = me.count; first = me.first;
+      fitted = (int)count >= P.min_points;
+      mz = (float)me.m[2];
+      const bool has_lo = (v > 0) && (S.in[tid].key >> 16) == (key >> 16);
+      const bool has_hi = (v + 1 < V) && (S.in[tid + 2].key >> 16) == (key >> 16);
       head = !has_lo;
       if (fitted) {
+        flags = GNDT_F_FITTED;
+        bool up = false, down = false;
+        const bool ordered = (P.demand == GNDT_DEMAND_SLOPE);
+        if (has_hi && (S.in[tid + 2].key & 0xFFFFu) == (key & 0xFFFFu) + 1) {
+          const VoxMoments &hi = S.in[tid + 2];
+          const bool seen = (int)hi.count >= P.min_points && (!ordered || hi.first < first);
+          up = fabsf(__fsub_rn(seen ? (float)hi.m[2] : 0.f, mz)) > P.slope_interval;
+        }
+        if (ordered && has_lo && (S.in[tid].key & 0xFFFFu) + 1 == (key & 0xFFFFu)) {
+          const VoxMoments &lo = S.in[tid];
+          const bool seen = (int)lo.count >= P.min_points && lo.first < first;
+          down = fabsf(__fsub_rn(seen ? (float)lo.m[2] : 0.f, mz)) > P.slope_interval;
+        }
+        if (up) flags |= GNDT_F_UP;
+        if (down) flags |= GNDT_F_DOWN;
+        if (P.demand == GNDT_DEMAND_TRUE || !up) flags |= GNDT_F_SLOPE;
+      }
+      if (head) flags |= GNDT_F_COLUMN_HEAD;
+    }
+    const bool slope = (flags & GNDT_F_SLOPE) != 0;
+    const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
+    u32 total = 0;
+    const u32 exc = block_exclusive_scan_256(packed, S.warp_sums, &total);
+    if (tid < 32) {  // warp 0 resolves the (columns, slopes) prefix of this block, 32 blocks per round trip
+      const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
+      const u64 pre = warp_lookback_u64(blk_state, (int)blk, mine, &ctl->err);
+      if (tid == 0) {
+        S.prefix = pre;
+        if (blk == n_blocks - 1) {
+          const u64 incl = pre + mine;
+          ctl->n_columns = (u32)(incl >> 31);
+          ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
+        }
+      }
+    }
+    const u32 fitted_cnt = __syncthreads_count(live && fitted);
+    if (tid == 0 && fitted_cnt) atomicAdd(&ctl->n_fitted, fitted_cnt);
+
+    // ---- phase 2: finish the voxel (binary32 mean / scatter, eigen) into shared memory
+    if (live) {
+      const u32 cols_before = (u32)(S.prefix >> 31) + (exc >> 16);
+      const u32 slopes_before = (u32)(S.prefix & 0x7FFFFFFFu) + (exc & 0xFFFFu);
+      const u32 col_idx = cols_before + (head ? 1u : 0u) - 1u;
+      float f[24];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) f[i] = 0.f;
+      u32 *u = reinterpret_cast<u32 *>(f);
+      const int cx = (int)(u32)(key >> 32) - kIdxBias, cy = (int)((u32)(key >> 16) & 0xFFFFu) - kIdxBias,
+                cz = (int)((u32)key & 0xFFFFu) - kIdxBias;
+      u[0] = (u32)signed_index(cx); u[1] = (u32)signed_index(cy); u[2] = (u32)signed_index(cz);
+      u[3] = count; u[4] = first;
+      if (fitted) {
+        const VoxMoments &me = S.in[tid + 1];
         f[5] = (float)me.m[0]; f[6] = (float)me.m[1]; f[7] = mz;
         double a[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-          float s = (float)me.s[k];
-          if (P.normalize_cov) s = __fdiv_rn(s, (float)me.count);
-          f[8 + k] = s;
-          a[k] = (double)s;  // the reference's solver sees the binary32 matrix (map2D.h:111)
+          float sc = (float)me.s[k];
+          if (P.normalize_cov) sc = __fdiv_rn(sc, (float)count);
+          f[8 + k] = sc;
+          a[k] = (double)sc;  // the reference's solver sees the binary32 matrix (map2D.h:111)
         }
         double w[3], Vv[3][3];
         eig3_sym(a, w, Vv);
@@ -224,66 +280,36 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
         f[18] = (float)(k == 0 ? Vv[1][0] : (k == 1 ? Vv[1][1] : Vv[1][2]));
         f[19] = (float)(k == 0 ? Vv[2][0] : (k == 1 ? Vv[2][1] : Vv[2][2]));
         f[20] = rough;
-        flags = GNDT_F_FITTED;
-        bool up = false, down = false;
-        const bool ordered = (P.demand == GNDT_DEMAND_SLOPE);
-        if (has_hi && (hi_key & 0xFFFFu) == (me.key & 0xFFFFu) + 1) {
-          const bool seen = (int)hi_count >= P.min_points && (!ordered || hi_first < me.first);
-          up = fabsf(__fsub_rn(seen ? hi_mz : 0.f, mz)) > P.slope_interval;
-        }
-        if (ordered && has_lo && (lo_key & 0xFFFFu) + 1 == (me.key & 0xFFFFu)) {
-          const bool seen = (int)lo_count >= P.min_points && lo_first < me.first;
-          down = fabsf(__fsub_rn(seen ? lo_mz : 0.f, mz)) > P.slope_interval;
-        }
-        if (up) flags |= GNDT_F_UP;
-        if (down) flags |= GNDT_F_DOWN;
-        if (P.demand == GNDT_DEMAND_TRUE || !up) flags |= GNDT_F_SLOPE;
       }
-      if (head) flags |= GNDT_F_COLUMN_HEAD;
-    }
-    const bool slope = (flags & GNDT_F_SLOPE) != 0;
-    const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
-    u32 total = 0;
-    const u32 exc = block_exclusive_scan_256(packed, warp_sums, &total);
-    if (tid < 32) {  // warp 0 resolves the (columns, slopes) prefix of this block, 32 blocks per round trip
-      const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
-      const u64 pre = warp_lookback_u64(blk_state, (int)blk, mine, &ctl->err);
-      if (tid == 0) {
-        s_prefix = pre;
-        if (blk == n_blocks - 1) {
-          const u64 incl = pre + mine;
-          ctl->n_columns = (u32)(incl >> 31);
-          ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
-        }
-      }
-    }
-    const u32 fitted_cnt = __syncthreads_count(live && (flags & GNDT_F_FITTED));
-    if (tid == 0 && fitted_cnt) atomicAdd(&ctl->n_fitted, fitted_cnt);
-    if (!live) continue;
-    const u32 cols_before = (u32)(s_prefix >> 31) + (exc >> 16);
-    const u32 slopes_before = (u32)(s_prefix & 0x7FFFFFFFu) + (exc & 0xFFFFu);
-    const u32 col_idx = cols_before + (head ? 1u : 0u) - 1u;
-    u[21] = flags; u[22] = col_idx; u[23] = slope ? slopes_before : 0xFFFFFFFFu;
-    float4 *dst = reinterpret_cast<float4 *>(table + v);
+      u[21] = flags; u[22] = col_idx; u[23] = slope ? slopes_before : 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-    if (slope) {
-      float4 *d = reinterpret_cast<float4 *>(slopes + slopes_before);
-      d[0] = make_float4(f[0], f[1], f[2], f[5]);          // sx sy sz mean.x
-      d[1] = make_float4(f[6], f[7], f[17], f[18]);        // mean.y mean.z normal.x normal.y
-      d[2] = make_float4(f[19], f[20], __uint_as_float(flags), __uint_as_float((u32)v));
+      for (int i = 0; i < 6; ++i) S.out[tid * 6 + i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      vfirst[v] = first;
+      if (slope) {
+        float4 *d = reinterpret_cast<float4 *>(slopes + slopes_before);
+        d[0] = make_float4(f[0], f[1], f[2], f[5]);          // sx sy sz mean.x
+        d[1] = make_float4(f[6], f[7], f[17], f[18]);        // mean.y mean.z normal.x normal.y
+        d[2] = make_float4(f[19], f[20], __uint_as_float(flags), __uint_as_float(v));
+      }
+      if (head) {
+        float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
+        d[0] = make_float4(f[0], f[1], f[4], __uint_as_float(v));                   // sx sy first voxel_begin
+        d[1] = make_float4(0.f, __uint_as_float(slopes_before), 0.f, 0.f);          // count slope_begin count rsvd
+      }
     }
-    if (head) {
-      float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
-      d[0] = make_float4(f[0], f[1], f[4], __uint_as_float((u32)v));                // sx sy first voxel_begin
-      d[1] = make_float4(0.f, __uint_as_float(slopes_before), 0.f, 0.f);            // count slope_begin count rsvd
+    // ---- the 256 records leave shared memory as one TMA bulk store
+    tma_store_fence();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_1d(table + v0, S.out, cnt * (u32)sizeof(gndt_voxel));
+      tma_store_wait_read();  // out[] may be overwritten after the next barrier
     }
   }
 }
 
 // K4b: one thread per column: extents, first-seen index (position in the reference's
 // morton_list, src/receiver.cpp:70) and the x-row directory used by the edge search.
-__global__ void column_finish_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_table_fixed,
+__global__ void column_finish_kernel(Ctl *ctl, const gndt_voxel *table, const u32 *vfirst, u32 n_table_fixed,
                                      gndt_column *columns, u32 *row_start, u32 *row_end, int cx_base_fixed,
                                      int use_fixed_base) {
   const u32 V = n_table_fixed ? n_table_fixed : ctl->n_voxels;
@@ -294,7 +320,9 @@ __global__ void column_finish_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_ta
     const u32 v_end = (c + 1 < C) ? columns[c + 1].voxel_begin : V;
     const u32 s_end = (c + 1 < C) ? columns[c + 1].slope_begin : S;
     u32 first = 0xFFFFFFFFu;
-    for (u32 v = col.voxel_begin; v < v_end; ++v) first = min(first, table[v].first_index);
+    // compact first-index array when the caller has one (main path), else the records
+    if (vfirst) for (u32 v = col.voxel_begin; v < v_end; ++v) first = min(first, vfirst[v]);
+    else for (u32 v = col.voxel_begin; v < v_end; ++v) first = min(first, table[v].first_index);
     columns[c].first_index = first;
     columns[c].voxel_count = v_end - col.voxel_begin;
     columns[c].slope_count = s_end - col.slope_begin;
@@ -347,15 +375,21 @@ __device__ __forceinline__ bool cell_reachable(const gndt_column &c, const gndt_
 __global__ void __launch_bounds__(256)
 edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column *columns,
              const u32 *row_start, const u32 *row_end, int cx_base_fixed, int cx_max_fixed, int use_fixed,
-             u32 vox_begin, u32 vox_end, DevParams P) {
+             u32 vox_begin, u32 vox_end, const int *halo_rows, int n_halo, DevParams P) {
   const u32 S = ctl->n_slopes, C = ctl->n_columns;
   const int cx_base = use_fixed ? cx_base_fixed : ctl->cx_min;
   const int cx_max = use_fixed ? cx_max_fixed : ctl->cx_max;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
     gndt_slope me = slopes[i];
-    if (me.voxel < vox_begin || me.voxel >= vox_end) continue;
-    const u32 ci = table[me.voxel].column;
     const int cx = contiguous_index(me.sx), cy = contiguous_index(me.sy);
+    if (me.voxel < vox_begin || me.voxel >= vox_end) {
+      // outside the caller's range: still refreshed when it lies on a strip-boundary x row
+      // (multi-GPU halo: those rows were labelled by their owner without their neighbour strip)
+      bool halo = false;
+      for (int k = 0; k < n_halo; ++k) halo |= (halo_rows[k] == cx);
+      if (!halo) continue;
+    }
+    const u32 ci = table[me.voxel].column;
     const float n[3] = {me.normal[0], me.normal[1], me.normal[2]};
     u32 bits = 0;
     if (ci > 0) {  // left: cy-1

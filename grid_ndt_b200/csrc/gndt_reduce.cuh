@@ -20,7 +20,7 @@ namespace gndt {
 constexpr int kRedThreads = 256;
 constexpr int kRedItems = 8;
 constexpr int kRedTile = kRedThreads * kRedItems;  // 2048 points
-constexpr int kLongRun = 64;                        // longer runs are reduced by the whole CTA
+constexpr int kLongRun = 32;                        // longer runs are reduced by a whole warp each
 constexpr int kMaxLong = kRedTile / kLongRun;
 
 struct Moments {
@@ -353,14 +353,15 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
   }
   __syncthreads();
 
-  // ---- long runs (heavy voxels): the whole CTA reduces each one
+  // ---- longer runs (large cells, heavy voxels): one WARP per run, lanes stride over the
+  //      run's points, fixed xor-shuffle tree (deterministic), no CTA-wide barriers
   const int n_long = (int)S.n_long;
-  for (int l = 0; l < n_long; ++l) {
+  for (int l = warp; l < n_long; l += kRedThreads / 32) {
     const int j = S.long_list[l];
     const int s = S.run_start[j], e = S.run_start[j + 1];
     const float4 p0 = S.pts[s];
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = s + tid; i < e; i += kRedThreads) {
+    for (int i = s + lane; i < e; i += 32) {
       const float4 p = S.pts[i];
       const double dx = (double)p.x - (double)p0.x, dy = (double)p.y - (double)p0.y, dz = (double)p.z - (double)p0.z;
       acc[0] += dx; acc[1] += dy; acc[2] += dz;
@@ -368,21 +369,11 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
-    if (lane == 0)
-#pragma unroll
-      for (int k = 0; k < 9; ++k) S.red[warp][k] = acc[k];
-    __syncthreads();
-    if (tid == 0) {
-      double t[9];
-      for (int k = 0; k < 9; ++k) {
-        t[k] = 0;
-        for (int w2 = 0; w2 < 8; ++w2) t[k] += S.red[w2][k];
-      }
+    if (lane == 0) {
       Moments mo;
-      close_moments(mo, (double)(e - s), p0, t, t + 3);
+      close_moments(mo, (double)(e - s), p0, acc, acc + 3);
       emit(j, mo);
     }
-    __syncthreads();
   }
 }
 

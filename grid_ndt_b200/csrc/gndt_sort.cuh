@@ -47,27 +47,6 @@ struct __align__(128) SortSmem {
 };
 static_assert((kMaxPasses - 1) * kRadixBins <= kSortTile, "later-digit histograms alias slot[]");
 
-// ---- TMA bulk copy + mbarrier (sm_90+; a lone CTA is a cluster of one) ------------------
-__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, u32 bytes, unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, u32 parity) {
-  for (u32 spins = 0; spins < kSpinLimit; ++spins) {
-    u32 done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    if (done) return true;
-  }
-  return false;
-}
-
 // Load point i of a strided cloud (first 12 bytes of each record are x,y,z).
 __device__ __forceinline__ float4 load_point(const float *in, size_t stride_f, size_t i, bool vec) {
   if (vec) return ld_stream(reinterpret_cast<const float4 *>(in) + i);

@@ -2,11 +2,15 @@
 
 Everything up to and including the surface labels depends only on the points of one x-y
 column, so strips need no exchange while they are built.  NCCL is used
-once per build, to all-gather the finished strip tables so that every rank (and the host
-planner behind it) holds the whole map; the neighbour-reachability bits of the columns on
-strip boundaries are then recomputed against the gathered table (their 1-cell halo).
-torch.distributed is only the plumbing (process group, streams, device buffers).
+once per build: the strip sizes are all-gathered (the only host synchronisation), then every
+rank sends its finished records straight out of the builder's table into the other ranks'
+copy of the whole map (batched point-to-point = an all-gather with uneven sizes, no padding,
+no staging copies).  The neighbour-reachability bits of the columns on strip boundaries are
+then recomputed against the gathered table — by every rank for every boundary row, so no
+second exchange is needed.  torch.distributed is only the plumbing (process group, streams,
+device buffers).
 """
+import ctypes as C
 from typing import Optional
 
 import numpy as np
@@ -14,7 +18,8 @@ import torch
 import torch.distributed as dist
 
 from ._abi import VOXEL_DTYPE
-from .builder import TwoDmap
+from ._lib import lib
+from .builder import TwoDmap, _check
 
 REC = VOXEL_DTYPE.itemsize  # 96
 
@@ -28,7 +33,8 @@ class TiledTwoDmap:
         self.map = TwoDmap(res, zres, device=device)
         self.map.setInterval(interval)
         self.device = torch.device("cuda", self.map._device)
-        self._gathered = None
+        self._counts = torch.zeros(world, dtype=torch.int32, device=self.device)
+        self._table = None
         self.offsets = None
 
     def plan(self, cloud, origin=None) -> np.ndarray:
@@ -39,11 +45,11 @@ class TiledTwoDmap:
         return self.map.plan_tiles(cloud, self.world)
 
     def build(self, cloud, demand="slope", origin=None, cuts=None, filter_points=True):
-        """Build this rank's strip and all-gather the strips.  `cloud` may be the whole
-        cloud (filter_points=True: points of other strips are dropped on the device) or
-        only this strip's share.  Returns (gathered table tensor [V_total, 96] uint8,
-        offsets[world+1])."""
-        m = self.map
+        """Build this rank's strip and assemble the whole map on every rank.  `cloud` may be
+        the whole cloud (filter_points=True: points of other strips are dropped on the
+        device) or only this strip's share.  Returns (table tensor [V_total, 96] uint8 on
+        this rank's GPU, offsets[world+1])."""
+        m, L = self.map, lib()
         if origin is not None:
             m.setCloudFirst(origin)
         if cuts is not None and filter_points:
@@ -51,31 +57,46 @@ class TiledTwoDmap:
         else:
             m.setTile(0, 0)
         m.uniformDivision(cloud)
-        m.create2DMap(demand)
-        ptr, n = m.device_voxels()
-        local = _as_tensor(ptr, max(n, 1) * REC, self.device)[: n * REC]
-        # (1)+(2) strip sizes, then a padded all-gather of the finished records
-        table, self.offsets = allgather_strips(local, self.world, self.group)
-        counts = np.diff(self.offsets)
-        total, vmax = int(self.offsets[-1]), int(counts.max())
-        # (3) halo: reachability bits of this strip against the whole map
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        m.label_edges(table.data_ptr(), total, int(self.offsets[self.rank]), n, st)
-        # (4) publish the refreshed flag words of this strip (4 B per voxel)
-        tv = table.view(torch.int32).view(-1, REC // 4)[:total]
-        my_flags = torch.zeros(max(vmax, 1), dtype=torch.int32, device=self.device)
-        my_flags[:n] = tv[self.offsets[self.rank]: self.offsets[self.rank] + n, 21]
-        all_flags = torch.empty(self.world * max(vmax, 1), dtype=torch.int32, device=self.device)
-        dist.all_gather_into_tensor(all_flags, my_flags, group=self.group)
+        m.create2DMap(demand)  # asynchronous
+        # (1) strip sizes: all-gather the device-side voxel counts; the .cpu() below is the
+        #     only host synchronisation of the whole step
+        p_cnt, p_tab, cap = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _check(m._h, L.gndt_device_count_ptr(m._h, C.byref(p_cnt)))
+        _check(m._h, L.gndt_device_table_ptr(m._h, C.byref(p_tab), C.byref(cap)))
+        mine = _as_tensor(p_cnt.value, 4, self.device).view(torch.int32)
+        dist.all_gather_into_tensor(self._counts, mine, group=self.group)
+        counts = self._counts.cpu().numpy().astype(np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+        total, n = int(self.offsets[-1]), int(counts[self.rank])
+        # (2) records: straight from the builder's table into every rank's map
+        if self._table is None or self._table.numel() < max(total, 1) * REC:
+            self._table = torch.empty(int(max(total, 1) * 1.25) * REC, dtype=torch.uint8, device=self.device)
+        table = self._table
+        local = _as_tensor(p_tab.value, max(n, 1) * REC, self.device)[: n * REC]
+        lo = int(self.offsets[self.rank]) * REC
+        ops = []
         for r in range(self.world):
-            c = int(counts[r])
-            tv[self.offsets[r]: self.offsets[r] + c, 21] = all_flags[r * vmax: r * vmax + c]
-        self._gathered = table
+            if r == self.rank or counts[r] == 0:
+                continue
+            ops.append(dist.P2POp(dist.irecv, table[int(self.offsets[r]) * REC: int(self.offsets[r + 1]) * REC], r, group=self.group))
+        if n:
+            for r in range(self.world):
+                if r != self.rank:
+                    ops.append(dist.P2POp(dist.isend, local, r, group=self.group))
+            table[lo: lo + n * REC].copy_(local, non_blocking=True)
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        # (3) halo: reachability bits of this strip and of every strip-boundary row against the
+        #     whole map, in one pass
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        off = (C.c_uint64 * (self.world + 1))(*[int(x) for x in self.offsets])
+        _check(m._h, L.gndt_label_edges_strips(m._h, table.data_ptr(), off, self.world, self.rank, st))
         return table[: total * REC].view(-1, REC), self.offsets
 
     def gathered_numpy(self) -> np.ndarray:
         total = int(self.offsets[-1])
-        return self._gathered[: total * REC].cpu().numpy().view(VOXEL_DTYPE).reshape(-1)
+        return self._table[: total * REC].cpu().numpy().view(VOXEL_DTYPE).reshape(-1)
 
     def close(self):
         self.map.close()
@@ -83,8 +104,10 @@ class TiledTwoDmap:
 
 def allgather_strips(local: torch.Tensor, world: int, group=None):
     """All-gather variable-length strip tables (flat uint8, 96 B records) into one compact
-    table in rank order.  Device-agnostic: NCCL on CUDA tensors, gloo on CPU tensors (the
-    CPU form is what the world_size-2 unit test exercises).  Returns (table, offsets)."""
+    table in rank order with collectives only (sizes, then padded records).  Device-agnostic:
+    NCCL on CUDA tensors, gloo on CPU tensors — the CPU form is what the world_size-2 unit test
+    exercises; TiledTwoDmap.build uses the unpadded point-to-point form of the same exchange.
+    Returns (table, offsets)."""
     dev = local.device
     n = local.numel() // REC
     cnt = torch.zeros(world, dtype=torch.int64, device=dev)

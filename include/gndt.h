@@ -216,6 +216,16 @@ int gndt_device_voxels(gndt_handle *h, const gndt_voxel **dptr, size_t *n);
  */
 int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin,
                      size_t count, void *stream);
+/* Same, for a table assembled from `n_strips` all-gathered x strips (strip r = records
+ * [offsets[r], offsets[r+1]), offsets on the host): refreshes strip `my_strip` AND every
+ * record on a strip-boundary x row (first/last row of each strip), so that after the call
+ * this GPU's copy of the whole map is consistent without any further exchange. */
+int gndt_label_edges_strips(gndt_handle *h, gndt_voxel *table, const uint64_t *offsets, int n_strips,
+                            int my_strip, void *stream);
+/* Stream-ordered (non-synchronising) access for collectives: device address of the voxel
+ * count of the last build, and of the table with its capacity in records. */
+int gndt_device_count_ptr(gndt_handle *h, const uint32_t **d_n_voxels);
+int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capacity);
 
 /*
  * Balanced x strips for `ntiles` GPUs: cuts[0..ntiles] in contiguous signed x index
