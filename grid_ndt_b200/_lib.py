@@ -58,6 +58,9 @@ SYMBOLS = {
     "gndt_device_voxels": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "gndt_label_edges": (_i, [_vp, _vp, _sz, _sz, _sz, _vp]),
     "gndt_label_edges_strips": (_i, [_vp, _vp, C.POINTER(C.c_uint64), _i, _i, _vp]),
+    "gndt_halo_pack": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "gndt_halo_edges": (_i, [_vp, _vp, _vp, _vp]),
+    "gndt_apply_strip_offsets": (_i, [_vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _i, _vp]),
     "gndt_device_count_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "gndt_device_table_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "gndt_plan_tiles": (_i, [_vp, _vp, _sz, _sz, _i, _i, C.POINTER(C.c_int32), _vp]),

@@ -628,6 +628,47 @@ int gndt_label_edges_strips(gndt_handle *h, gndt_voxel *table, const uint64_t *o
                           (size_t)(offsets[my_strip + 1] - offsets[my_strip]), offsets, n_strips, static_cast<cudaStream_t>(stream));
 }
 
+int gndt_halo_pack(gndt_handle *h, gndt_voxel *first_row_out, gndt_voxel *last_row_out, size_t cap_records, void *stream) {
+  if (!h || !first_row_out || !last_row_out || cap_records < 1) return GNDT_ERR_INVALID_ARG;
+  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  halo_pack_kernel<<<2, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_column *)h->columns.p, h->row_start,
+                                      h->row_end, first_row_out, last_row_out, (u32)cap_records);
+  h->launches += 1;
+  GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
+int gndt_halo_edges(gndt_handle *h, const gndt_voxel *from_prev, const gndt_voxel *from_next, void *stream) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  const DevParams dp = make_dev(h, h->params, h->cap_voxels);
+  halo_edges_kernel<<<grid_for(h, h->cap_voxels, 256, 8), 256, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
+                                                                        from_prev, from_next, dp);
+  h->launches += 1;
+  h->counts_valid = false;
+  GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
+int gndt_apply_strip_offsets(gndt_handle *h, gndt_voxel *table, const uint64_t *offsets, const uint32_t *col_offsets,
+                             const uint32_t *slope_offsets, int n_strips, void *stream) {
+  if (!h || !table || !offsets || !col_offsets || !slope_offsets || n_strips < 1) return GNDT_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  for (int r = 0; r < n_strips; ++r) {
+    const uint64_t cnt = offsets[r + 1] - offsets[r];
+    if (!cnt || (col_offsets[r] == 0 && slope_offsets[r] == 0)) continue;
+    strip_offsets_kernel<<<grid_for(h, cnt, 256, 8), 256, 0, st>>>(table, offsets[r], cnt, col_offsets[r], slope_offsets[r]);
+    h->launches += 1;
+  }
+  GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
 int gndt_device_count_ptr(gndt_handle *h, const uint32_t **d_n_voxels) {
   if (!h || !d_n_voxels) return GNDT_ERR_INVALID_ARG;
   if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }

@@ -425,3 +425,114 @@ edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column 
 }
 
 }  // namespace gndt
+
+// =======================================================================================
+// Multi-GPU halo: only the neighbour-reachability bits need data of another
+// strip, and only the first / last x row of a strip does.  Each strip packs those two rows,
+// swaps them with its neighbours, fixes its own boundary rows, and the records that are
+// then all-gathered are final.
+// =======================================================================================
+namespace gndt {
+
+struct HaloHeader {  // occupies the first 96-byte slot of a halo buffer
+  u32 count;         // records that follow (0 when the strip is empty or the row did not fit)
+  int cx;            // contiguous x index of the packed row
+  u32 overflow;      // row larger than the buffer: receiver must fall back to a full relabel
+  u32 pad[21];
+};
+static_assert(sizeof(HaloHeader) == sizeof(gndt_voxel), "header uses one record slot");
+
+// Pack the first x row into `first_out` and the last x row into `last_out` (each: header +
+// up to cap records).  One CTA per buffer copies cooperatively.
+__global__ void __launch_bounds__(256)
+halo_pack_kernel(const Ctl *ctl, const gndt_voxel *table, const gndt_column *columns, const u32 *row_start,
+                 const u32 *row_end, gndt_voxel *first_out, gndt_voxel *last_out, u32 cap) {
+  const bool last = blockIdx.x == 1;
+  gndt_voxel *out = last ? last_out : first_out;
+  HaloHeader *hdr = reinterpret_cast<HaloHeader *>(out);
+  const u32 V = ctl->n_voxels, C = ctl->n_columns;
+  u32 lo = 0, hi = 0;
+  int cx = 0;
+  if (V && C && !ctl->err) {
+    const int n_rows = ctl->cx_max - ctl->cx_min + 1;
+    if (!last) {
+      const u32 c_end = row_end[0];  // the strip's first row always exists when V > 0
+      lo = 0;
+      hi = (c_end < C) ? columns[c_end].voxel_begin : V;
+      cx = ctl->cx_min;
+    } else {
+      lo = columns[row_start[n_rows - 1]].voxel_begin;
+      hi = V;
+      cx = ctl->cx_max;
+    }
+  }
+  const u32 n = hi - lo;
+  const bool fits = n <= cap;
+  if (threadIdx.x == 0) { hdr->count = fits ? n : 0; hdr->cx = cx; hdr->overflow = fits ? 0u : 1u; }
+  if (!fits) return;
+  const float4 *src = reinterpret_cast<const float4 *>(table + lo);
+  float4 *dst = reinterpret_cast<float4 *>(out + 1);
+  for (u32 i = threadIdx.x; i < n * 6; i += blockDim.x) dst[i] = src[i];
+}
+
+// Does the halo row hold, in the column with contiguous y index `cy`, a Slope reachable from
+// (normal n, mean z)?  Halo records are sorted by (cy, cz); same four tests as cell_reachable.
+__device__ __forceinline__ bool halo_reachable(const gndt_voxel *halo, u32 n_halo, int cy, const float n[3], float mz,
+                                               const DevParams &P) {
+  u32 lo = 0, hi = n_halo;
+  while (lo < hi) {
+    const u32 mid = (lo + hi) >> 1;
+    if (contiguous_index(halo[mid].sy) < cy) lo = mid + 1; else hi = mid;
+  }
+  for (u32 v = lo; v < n_halo && contiguous_index(halo[v].sy) == cy; ++v) {
+    const gndt_voxel &t = halo[v];
+    if (!(t.flags & GNDT_F_SLOPE) || (t.flags & GNDT_F_UP)) continue;
+    if (!(t.rough <= P.rough_max)) continue;
+    const float tn[3] = {t.normal[0], t.normal[1], t.normal[2]};
+    if (!(count_angle(tn, n) <= P.angle_max_deg)) continue;
+    if (!(fabsf(__fsub_rn(t.mean[2], mz)) <= P.reach_height)) continue;
+    return true;
+  }
+  return false;
+}
+
+// Fix the forward/back reachability of this strip's boundary rows against the neighbours'
+// halo rows: `from_prev` = last row of the strip below in x, `from_next` = first row of the
+// strip above (either may be NULL at the ends of the map).
+__global__ void __launch_bounds__(256)
+halo_edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_voxel *from_prev,
+                  const gndt_voxel *from_next, DevParams P) {
+  const u32 S = ctl->n_slopes;
+  const int cx_lo = ctl->cx_min, cx_hi = ctl->cx_max;
+  const HaloHeader *hp = reinterpret_cast<const HaloHeader *>(from_prev), *hn = reinterpret_cast<const HaloHeader *>(from_next);
+  const bool use_prev = hp && hp->count && hp->cx == cx_lo - 1;  // adjacent x rows only
+  const bool use_next = hn && hn->count && hn->cx == cx_hi + 1;
+  if ((hp && hp->overflow) || (hn && hn->overflow)) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->err, kErrCapacity); return; }
+  if (!use_prev && !use_next) return;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+    const int cx = contiguous_index(slopes[i].sx);
+    if (cx != cx_lo && cx != cx_hi) continue;
+    const gndt_slope me = slopes[i];
+    const int cy = contiguous_index(me.sy);
+    const float n[3] = {me.normal[0], me.normal[1], me.normal[2]};
+    u32 bits = 0;
+    if (use_prev && cx == cx_lo && halo_reachable(from_prev + 1, hp->count, cy, n, me.mean[2], P)) bits |= GNDT_F_REACH_B;
+    if (use_next && cx == cx_hi && halo_reachable(from_next + 1, hn->count, cy, n, me.mean[2], P)) bits |= GNDT_F_REACH_F;
+    if (bits) {
+      slopes[i].flags = me.flags | bits;
+      table[me.voxel].flags |= bits;
+    }
+  }
+}
+
+// After the all-gather: make the strip-local `column` / `slope` indices of strip records
+// [begin, begin+count) global by adding the strip's offsets.
+__global__ void strip_offsets_kernel(gndt_voxel *table, u64 begin, u64 count, u32 col_off, u32 slope_off) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (u64)gridDim.x * blockDim.x) {
+    gndt_voxel *r = table + begin + i;
+    r->column += col_off;
+    if (r->slope != 0xFFFFFFFFu) r->slope += slope_off;
+  }
+}
+
+}  // namespace gndt

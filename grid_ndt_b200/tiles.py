@@ -1,14 +1,16 @@
 """Multi-GPU map build: one x strip of the map per GPU of a single box, one process per GPU.
 
 Everything up to and including the surface labels depends only on the points of one x-y
-column, so strips need no exchange while they are built.  NCCL is used
-once per build: the strip sizes are all-gathered (the only host synchronisation), then every
-rank sends its finished records straight out of the builder's table into the other ranks'
-copy of the whole map (batched point-to-point = an all-gather with uneven sizes, no padding,
-no staging copies).  The neighbour-reachability bits of the columns on strip boundaries are
-then recomputed against the gathered table — by every rank for every boundary row, so no
-second exchange is needed.  torch.distributed is only the plumbing (process group, streams,
-device buffers).
+column, so strips need no exchange while they are built.  The only cross-
+strip dependence is the forward/back reachability of the first and last x row of a strip, so
+those two rows (a thin halo, fixed-size buffers, no host round trip) are swapped with the two
+neighbour strips BEFORE the gather and each rank finishes its own boundary rows.  Then the
+strip sizes are all-gathered (the only host synchronisation of a build) and every rank sends
+its final records straight out of the builder's table into the other ranks' copy of the whole
+map (batched point-to-point = an all-gather with uneven sizes, no padding, no staging copies;
+measured faster than padded all_gather / broadcasts, tools/gather_bench.py).  Last, strip-local
+column / slope indices are made global by adding per-strip offsets.  torch.distributed is only
+the plumbing (process group, streams, device buffers).
 """
 import ctypes as C
 from typing import Optional
@@ -28,13 +30,16 @@ class TiledTwoDmap:
     """Strip r of `world` strips.  `cuts` are contiguous signed x column indices; strip r
     keeps columns with cuts[r] <= cx < cuts[r+1] (gndt_params.tile_lo/hi)."""
 
-    def __init__(self, res, zres, interval, rank: int, world: int, device: Optional[int] = None, group=None):
+    def __init__(self, res, zres, interval, rank: int, world: int, device: Optional[int] = None, group=None,
+                 halo_records: int = 32768):
         self.rank, self.world, self.group = rank, world, group
         self.map = TwoDmap(res, zres, device=device)
         self.map.setInterval(interval)
         self.device = torch.device("cuda", self.map._device)
-        self._counts = torch.zeros(world, dtype=torch.int32, device=self.device)
+        self._counts = torch.zeros(world * 4, dtype=torch.int32, device=self.device)
         self._table = None
+        self._halo = None
+        self.halo_records = halo_records  # capacity of one halo row (records); overflow is reported, not truncated
         self.offsets = None
 
     def plan(self, cloud, origin=None) -> np.ndarray:
@@ -48,7 +53,16 @@ class TiledTwoDmap:
         """Build this rank's strip and assemble the whole map on every rank.  `cloud` may be
         the whole cloud (filter_points=True: points of other strips are dropped on the
         device) or only this strip's share.  Returns (table tensor [V_total, 96] uint8 on
-        this rank's GPU, offsets[world+1])."""
+        this rank's GPU, offsets[world+1]).
+
+        Order of work (everything stream-ordered except the one size exchange):
+          1. local build of the strip (no communication: labels are per column)
+          2. thin halo: first / last x row swapped with the two neighbour strips, the strip's
+             own boundary rows get their cross-strip forward/back reachability bits
+          3. strip sizes all-gathered (the only host synchronisation)
+          4. the now-final records go straight from the builder's table into every rank's
+             copy of the map (batched point-to-point = all-gather with uneven sizes)
+          5. strip-local column / slope indices become global (add per-strip offsets)"""
         m, L = self.map, lib()
         if origin is not None:
             m.setCloudFirst(origin)
@@ -57,18 +71,39 @@ class TiledTwoDmap:
         else:
             m.setTile(0, 0)
         m.uniformDivision(cloud)
-        m.create2DMap(demand)  # asynchronous
-        # (1) strip sizes: all-gather the device-side voxel counts; the .cpu() below is the
-        #     only host synchronisation of the whole step
+        m.create2DMap(demand)  # (1) asynchronous
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        # (2) halo rows: fixed-size buffers so that no size has to be known on the host
+        slot = (self.halo_records + 1) * REC
+        if self._halo is None:
+            self._halo = torch.zeros(4 * slot, dtype=torch.uint8, device=self.device)
+        send_first, send_last, recv_prev, recv_next = (self._halo[i * slot:(i + 1) * slot] for i in range(4))
+        _check(m._h, L.gndt_halo_pack(m._h, send_first.data_ptr(), send_last.data_ptr(), self.halo_records, st))
+        ops = []
+        if self.rank > 0:
+            ops += [dist.P2POp(dist.isend, send_first, self.rank - 1, group=self.group),
+                    dist.P2POp(dist.irecv, recv_prev, self.rank - 1, group=self.group)]
+        if self.rank + 1 < self.world:
+            ops += [dist.P2POp(dist.isend, send_last, self.rank + 1, group=self.group),
+                    dist.P2POp(dist.irecv, recv_next, self.rank + 1, group=self.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        _check(m._h, L.gndt_halo_edges(m._h, recv_prev.data_ptr() if self.rank > 0 else None,
+                                       recv_next.data_ptr() if self.rank + 1 < self.world else None, st))
+        # (3) strip sizes: {n_voxels, n_columns, n_slopes, n_fitted} of every strip
         p_cnt, p_tab, cap = C.c_void_p(), C.c_void_p(), C.c_size_t()
         _check(m._h, L.gndt_device_count_ptr(m._h, C.byref(p_cnt)))
         _check(m._h, L.gndt_device_table_ptr(m._h, C.byref(p_tab), C.byref(cap)))
-        mine = _as_tensor(p_cnt.value, 4, self.device).view(torch.int32)
+        mine = _as_tensor(p_cnt.value, 16, self.device).view(torch.int32)
         dist.all_gather_into_tensor(self._counts, mine, group=self.group)
-        counts = self._counts.cpu().numpy().astype(np.int64)
+        counts4 = self._counts.cpu().numpy().astype(np.int64).reshape(self.world, 4)
+        counts = counts4[:, 0]
         self.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+        col_off = np.concatenate([[0], np.cumsum(counts4[:, 1])])[:-1].astype(np.uint32)
+        slope_off = np.concatenate([[0], np.cumsum(counts4[:, 2])])[:-1].astype(np.uint32)
         total, n = int(self.offsets[-1]), int(counts[self.rank])
-        # (2) records: straight from the builder's table into every rank's map
+        # (4) records: straight from the builder's table into every rank's map
         if self._table is None or self._table.numel() < max(total, 1) * REC:
             self._table = torch.empty(int(max(total, 1) * 1.25) * REC, dtype=torch.uint8, device=self.device)
         table = self._table
@@ -87,11 +122,12 @@ class TiledTwoDmap:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        # (3) halo: reachability bits of this strip and of every strip-boundary row against the
-        #     whole map, in one pass
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        # (5) global column / slope indices
         off = (C.c_uint64 * (self.world + 1))(*[int(x) for x in self.offsets])
-        _check(m._h, L.gndt_label_edges_strips(m._h, table.data_ptr(), off, self.world, self.rank, st))
+        co = (C.c_uint32 * self.world)(*[int(x) for x in col_off])
+        so = (C.c_uint32 * self.world)(*[int(x) for x in slope_off])
+        _check(m._h, L.gndt_apply_strip_offsets(m._h, table.data_ptr(), off, co, so, self.world, st))
+        self.strip_counts = counts4
         return table[: total * REC].view(-1, REC), self.offsets
 
     def gathered_numpy(self) -> np.ndarray:

@@ -222,9 +222,27 @@ int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t b
  * this GPU's copy of the whole map is consistent without any further exchange. */
 int gndt_label_edges_strips(gndt_handle *h, gndt_voxel *table, const uint64_t *offsets, int n_strips,
                             int my_strip, void *stream);
+/*
+ * Thin-halo protocol for x strips (no host synchronisation, all stream-ordered):
+ *   gndt_halo_pack  writes this strip's first and last x row into two caller buffers of
+ *                   (1 + cap_records) gndt_voxel slots each (slot 0 is a header);
+ *   the caller swaps them with the neighbour strips (rank-1 gets `first`, rank+1 `last`);
+ *   gndt_halo_edges completes the forward/back reachability bits of this strip's boundary
+ *                   rows from the neighbours' rows (NULL at the ends of the map).  A row
+ *                   that did not fit raises GNDT_ERR_CAPACITY at the next result query.
+ * After that the strip's records are final and can be all-gathered as they are;
+ * gndt_apply_strip_offsets then turns the strip-local `column` / `slope` indices of the
+ * gathered records into global ones (offsets = exclusive prefix sums over the strips).
+ */
+int gndt_halo_pack(gndt_handle *h, gndt_voxel *first_row_out, gndt_voxel *last_row_out, size_t cap_records,
+                   void *stream);
+int gndt_halo_edges(gndt_handle *h, const gndt_voxel *from_prev, const gndt_voxel *from_next, void *stream);
+int gndt_apply_strip_offsets(gndt_handle *h, gndt_voxel *table, const uint64_t *offsets,
+                             const uint32_t *col_offsets, const uint32_t *slope_offsets, int n_strips,
+                             void *stream);
 /* Stream-ordered (non-synchronising) access for collectives: device address of the voxel
  * count of the last build, and of the table with its capacity in records. */
-int gndt_device_count_ptr(gndt_handle *h, const uint32_t **d_n_voxels);
+int gndt_device_count_ptr(gndt_handle *h, const uint32_t **d_n_voxels); /* -> {n_voxels, n_columns, n_slopes, n_fitted} */
 int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capacity);
 
 /*

@@ -1,6 +1,7 @@
 """torchrun worker for the N>1 GPU test: every rank sees the whole cloud, plans the same
-balanced x strips, builds its strip, all-gathers over NCCL, relabels the halo, and the
-gathered map is compared with the oracle's untiled build (reach bits included)."""
+balanced x strips, builds its strip, swaps the thin halo with its neighbours, gathers the
+final records over NCCL, and the gathered map is compared with the oracle's untiled build
+(reach bits and global column / slope indices included)."""
 import os
 import sys
 
@@ -36,7 +37,9 @@ def main():
         assert len(got) == o.counts["n_voxels"], (len(got), o.counts)
         for f in ("sx", "sy", "sz", "count", "first_index"):
             assert np.array_equal(got[f], o.voxels[f]), f
-        assert np.array_equal(got["flags"] & 0x0F, o.voxels["flags"] & 0x0F)
+        assert np.array_equal(got["flags"] & 0x10F, o.voxels["flags"] & 0x10F)
+        assert np.array_equal(got["column"], o.voxels["column"]), "global column indices after the gather"
+        assert np.array_equal(got["slope"], o.voxels["slope"]), "global slope indices after the gather"
         reach_bad = int(((got["flags"] ^ o.voxels["flags"]) & _abi.F_REACH_ALL != 0).sum())
         assert reach_bad <= 5, f"reach bits differ on {reach_bad} voxels"
         assert sizes.min() > 0.5 * sizes.mean(), f"strips unbalanced: {sizes}"
