@@ -263,9 +263,11 @@ int grid_for(const gndt_handle *h, size_t work_items, int per_block, int max_wav
 int sync_counts(gndt_handle *h) {
   if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
   if (h->counts_valid) return GNDT_OK;
+  // stream-ordered behind the build and nothing else: no legacy-stream copy, so builds of other
+  // handles on other streams (a pipelined caller) keep running while this one is read back
+  GNDT_CUDA(h, cudaMemcpyAsync(&h->host_ctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->last_stream));
+  GNDT_CUDA(h, cudaMemcpyAsync(&h->host_tot, h->small.p, sizeof(Totals), cudaMemcpyDeviceToHost, h->last_stream));
   GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
-  GNDT_CUDA(h, cudaMemcpy(&h->host_ctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
-  GNDT_CUDA(h, cudaMemcpy(&h->host_tot, h->small.p, sizeof(Totals), cudaMemcpyDeviceToHost));
   if (h->host_ctl.err & kErrWatchdog) { h->err = "device watchdog tripped (look-back / TMA wait never resolved)"; return GNDT_ERR_INTERNAL; }
   if (h->host_ctl.err & kErrCapacity) { h->err = "voxel table capacity (max_voxels) exceeded"; return GNDT_ERR_CAPACITY; }
   h->counts_valid = true;
@@ -534,7 +536,11 @@ static int copy_out(gndt_handle *h, void *dst, size_t cap, int dst_mem, size_t *
                     size_t rec) {
   if (!dst && n) return GNDT_ERR_INVALID_ARG;
   if (n > cap) { h->err = "destination capacity too small"; return GNDT_ERR_CAPACITY; }
-  if (n) GNDT_CUDA(h, cudaMemcpy(dst, src, n * rec, dst_mem == GNDT_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
+  if (n) {
+    GNDT_CUDA(h, cudaMemcpyAsync(dst, src, n * rec, dst_mem == GNDT_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                 h->last_stream));
+    GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  }
   if (n_out) *n_out = n;
   return GNDT_OK;
 }
