@@ -286,19 +286,22 @@ int front_end(gndt_handle *h, cudaStream_t st, const float *d_in, size_t n, size
   // K2: partition passes (pass p writes buffer A when p is even, B when odd)
   const int tiles = (int)((n + kSortTile - 1) / kSortTile);
   float4 *A = static_cast<float4 *>(h->buf_a.p), *B = static_cast<float4 *>(h->buf_b.p);
-  sort_pass_kernel<true><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A,
-                                                                        h->lb, h->hist, dp);
+  // the division mode is a template argument (two instantiations), not a run-time select
+  auto *first_pass = dp.fast_div ? sort_pass_kernel<true, true> : sort_pass_kernel<true, false>;
+  auto *next_pass = dp.fast_div ? sort_pass_kernel<false, true> : sort_pass_kernel<false, false>;
+  first_pass<<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A, h->lb, h->hist, dp);
   for (int p = 1; p < kMaxPasses; ++p) {
     const float4 *src = (p & 1) ? A : B;
     float4 *dst = (p & 1) ? B : A;
-    sort_pass_kernel<false><<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
+    next_pass<<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
         h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins, h->hist, dp);
   }
   h->launches += kMaxPasses;
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));
   // K3: per-voxel moments
   const int rtiles = (int)((n + kRedTile - 1) / kRedTile);
-  reduce_kernel<<<rtiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, out, h->carry, h->tile_state, dp);
+  auto *reduce = dp.fast_div ? reduce_kernel<true> : reduce_kernel<false>;
+  reduce<<<rtiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, out, h->carry, h->tile_state, dp);
   fixup_kernel<<<grid_for(h, (size_t)rtiles * 32, 128, 16), 128, 0, st>>>(h->ctl, out, h->carry);
   h->launches += 2;
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_REDUCE], st));
@@ -379,9 +382,12 @@ int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   for (int i = 0; i < EV_COUNT; ++i)
     if ((e = cudaEventCreate(&h->ev[i])) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
-  e = cudaFuncSetAttribute(sort_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
+  e = cudaFuncSetAttribute(sort_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(finalize_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem));
   if (e != cudaSuccess) { g_create_error = std::string("kernel image for sm_100a not loadable on this device: ") + cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
   int rc = verify_fast_div(h, h->params.grid_len, h->div[0]);

@@ -17,10 +17,16 @@
 
 namespace gndt {
 
+#ifndef GNDT_RED_MINBLOCKS
+#define GNDT_RED_MINBLOCKS 4
+#endif
+#ifndef GNDT_RED_LONGRUN
+#define GNDT_RED_LONGRUN 64
+#endif
 constexpr int kRedThreads = 256;
 constexpr int kRedItems = 8;
 constexpr int kRedTile = kRedThreads * kRedItems;  // 2048 points
-constexpr int kLongRun = 32;                        // longer runs are reduced by a whole warp each
+constexpr int kLongRun = GNDT_RED_LONGRUN;          // longer runs are reduced by a whole warp each
 constexpr int kMaxLong = kRedTile / kLongRun;
 
 struct Moments {
@@ -165,9 +171,10 @@ struct RedSmem {
   u32 n_long, tile_id, n_runs, vox_base;
 };
 
+template <bool FAST>
 __device__ __forceinline__ u64 point_key(const float4 &p, const float o[3], const DevParams &P) {
   int cx, cy, cz;
-  point_indices(p.x, p.y, p.z, o, P, cx, cy, cz);
+  point_indices_t<FAST>(p.x, p.y, p.z, o, P, cx, cy, cz);
   return voxel_key(cx, cy, cz);
 }
 
@@ -212,7 +219,8 @@ __device__ __forceinline__ u32 warp_lookback_u32(u32 *state, int tile, u32 my_co
 
 // K3: one CTA per tile of 2048 sorted points -> raw moments of every voxel whose run starts
 // in the tile; partial runs at the tile edges go to the carry array.
-__global__ void __launch_bounds__(kRedThreads, 3)
+template <bool FAST>
+__global__ void __launch_bounds__(kRedThreads, GNDT_RED_MINBLOCKS)
 reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mom, TileCarry *carry,
               u32 *tile_state, DevParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -245,14 +253,14 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
     key[k] = ~0ull;
     if (i < cnt) {
       S.pts[i] = pt[k];
-      key[k] = point_key(pt[k], o, P);
+      key[k] = point_key<FAST>(pt[k], o, P);
     }
     if (lane == 31) S.row_last_key[k][warp] = key[k];
     if (i == 0) S.first_key = key[k];
     if (i == cnt - 1) S.last_key = key[k];
   }
-  if (tid == 0) S.prev_key = (base > 0) ? point_key(edge, o, P) : ~0ull;
-  if (tid == 32) S.next_key = (base + cnt < M) ? point_key(edge, o, P) : ~0ull;
+  if (tid == 0) S.prev_key = (base > 0) ? point_key<FAST>(edge, o, P) : ~0ull;
+  if (tid == 32) S.next_key = (base + cnt < M) ? point_key<FAST>(edge, o, P) : ~0ull;
   __syncthreads();
 
   // ---- run heads (position 0 always starts a run of this tile)
@@ -340,7 +348,7 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
       return;
     }
     if (slot >= P.max_voxels) { atomicOr(&ctl->err, kErrCapacity); return; }
-    store_moments(mom + slot, point_key(S.pts[s], o, P), __float_as_uint(S.pts[s].w), mo);
+    store_moments(mom + slot, point_key<FAST>(S.pts[s], o, P), __float_as_uint(S.pts[s].w), mo);
     if (open_end) {
       my_carry->tail_slot = slot;
       atomicOr(&my_carry->flags, kCarryHasTail);

@@ -200,7 +200,7 @@ __global__ void plan_kernel(Ctl *ctl) {
 //  4. copy-out: consecutive threads gather their point through the permutation and write
 //     consecutive addresses inside a digit run
 // ---------------------------------------------------------------------------------------
-template <bool FIRST>
+template <bool FIRST, bool FAST>
 __global__ void __launch_bounds__(kSortThreads, GNDT_SORT_MINBLOCKS)
 sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_t n_in, size_t start,
                  const float4 *src, float4 *dst, u32 *lb, u32 *hist_all, DevParams P) {
@@ -276,7 +276,7 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
       const float4 e = S.in[i];
       int cx, cy, cz;
       if (FIRST) {
-        bool ok = point_indices(e.x, e.y, e.z, o, P, cx, cy, cz);
+        bool ok = point_indices_t<FAST>(e.x, e.y, e.z, o, P, cx, cy, cz);
         if (ok && tiled && (cx < P.tile_lo || cx >= P.tile_hi)) ok = false;
         if (ok) {
           dg[k] = first_digit(cz);
@@ -286,7 +286,7 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
             if (q < n_passes) atomicAdd(&later_hist[(q - 1) * kRadixBins + ((u32)(key >> q_shift[q]) & q_mask[q])], 1u);
         }
       } else {
-        point_indices_masked(e.x, e.y, e.z, o, P, need, cx, cy, cz);
+        point_indices_masked_t<FAST>(e.x, e.y, e.z, o, P, need, cx, cy, cz);
         u32 d = 0;
         if (need & 1) d |= ((u32)(cx - L.cx_min) >> rs_x) << ls_x;
         if (need & 2) d |= ((u32)(cy - L.cy_min) >> rs_y) << ls_y;
