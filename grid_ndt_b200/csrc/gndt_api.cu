@@ -55,11 +55,12 @@ struct gndt_handle {
   u32 *hist = nullptr;
   u32 *row_start = nullptr, *row_end = nullptr;
   u32 *lb = nullptr;
+  u64 *glb = nullptr;   // look-back group words [kMaxPasses][sort_groups][256]
   u32 *tile_state = nullptr;
   TileCarry *carry = nullptr;
   u64 *blk_state = nullptr;
   size_t zero_bytes_used = 0;
-  size_t sort_tiles = 0, red_tiles = 0, label_blocks = 0;
+  size_t sort_tiles = 0, sort_groups = 0, red_tiles = 0, label_blocks = 0;
   // foreign-table scratch (gndt_label_edges)
   Buffer f_slopes, f_columns, f_zero;
   // state
@@ -226,6 +227,7 @@ int reserve(gndt_handle *h, size_t n, size_t cap_vox, bool host_input, size_t st
   h->cap_points = n;
   h->cap_voxels = cap_vox;
   h->sort_tiles = (n + kSortTile - 1) / kSortTile;
+  h->sort_groups = (h->sort_tiles + kSortGroup - 1) / kSortGroup;
   h->red_tiles = (n + kRedTile - 1) / kRedTile;
   h->label_blocks = (cap_vox + kLabelThreads - 1) / kLabelThreads;
   size_t off = 0;
@@ -235,6 +237,7 @@ int reserve(gndt_handle *h, size_t n, size_t cap_vox, bool host_input, size_t st
   const size_t o_rs = carve(65536 * sizeof(u32));
   const size_t o_re = carve(65536 * sizeof(u32));
   const size_t o_lb = carve((size_t)kMaxPasses * h->sort_tiles * kRadixBins * sizeof(u32));
+  const size_t o_glb = carve((size_t)kMaxPasses * h->sort_groups * kRadixBins * sizeof(u64));
   const size_t o_ts = carve(h->red_tiles * sizeof(u32));
   const size_t o_ca = carve(h->red_tiles * sizeof(TileCarry));
   const size_t o_bs = carve(h->label_blocks * sizeof(u64));
@@ -245,6 +248,7 @@ int reserve(gndt_handle *h, size_t n, size_t cap_vox, bool host_input, size_t st
   h->row_start = reinterpret_cast<u32 *>(z + o_rs);
   h->row_end = reinterpret_cast<u32 *>(z + o_re);
   h->lb = reinterpret_cast<u32 *>(z + o_lb);
+  h->glb = reinterpret_cast<u64 *>(z + o_glb);
   h->tile_state = reinterpret_cast<u32 *>(z + o_ts);
   h->carry = reinterpret_cast<TileCarry *>(z + o_ca);
   h->blk_state = reinterpret_cast<u64 *>(z + o_bs);
@@ -289,12 +293,13 @@ int front_end(gndt_handle *h, cudaStream_t st, const float *d_in, size_t n, size
   // the division mode is a template argument (two instantiations), not a run-time select
   auto *first_pass = dp.fast_div ? sort_pass_kernel<true, true> : sort_pass_kernel<true, false>;
   auto *next_pass = dp.fast_div ? sort_pass_kernel<false, true> : sort_pass_kernel<false, false>;
-  first_pass<<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A, h->lb, h->hist, dp);
+  first_pass<<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A, h->lb, h->glb, h->hist, dp);
   for (int p = 1; p < kMaxPasses; ++p) {
     const float4 *src = (p & 1) ? A : B;
     float4 *dst = (p & 1) ? B : A;
     next_pass<<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
-        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins, h->hist, dp);
+        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins,
+        h->glb + (size_t)p * h->sort_groups * kRadixBins, h->hist, dp);
   }
   h->launches += kMaxPasses;
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));

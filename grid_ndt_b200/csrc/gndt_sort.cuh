@@ -32,6 +32,12 @@ constexpr int kSortItems = GNDT_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 3072 points = 48 KB staged
 constexpr int kSortWarps = kSortThreads / 32;
 static_assert(kSortThreads >= kRadixBins && kSortTile <= 65536, "tile shape");
+#ifndef GNDT_SORT_GROUP
+#define GNDT_SORT_GROUP 16
+#endif
+constexpr int kSortGroup = GNDT_SORT_GROUP;  // tiles per look-back group
+constexpr int kGroupSumBits = 26;            // group word: arrivals << 26 | sum of the tiles' digit counts
+static_assert(kSortGroup >= 1 && kSortGroup < 64 && (long long)kSortGroup * kSortTile < (1ll << kGroupSumBits), "group word");
 
 struct __align__(128) SortSmem {
   float4 in[kSortTile];            // the tile, in arrival order (TMA destination)
@@ -203,7 +209,7 @@ __global__ void plan_kernel(Ctl *ctl) {
 template <bool FIRST, bool FAST>
 __global__ void __launch_bounds__(kSortThreads, GNDT_SORT_MINBLOCKS)
 sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_t n_in, size_t start,
-                 const float4 *src, float4 *dst, u32 *lb, u32 *hist_all, DevParams P) {
+                 const float4 *src, float4 *dst, u32 *lb, u64 *glb, u32 *hist_all, DevParams P) {
   extern __shared__ __align__(128) unsigned char smem_sort[];
   SortSmem &S = *reinterpret_cast<SortSmem *>(smem_sort);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -337,6 +343,7 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
       tile_count += t;
     }
     st_relaxed(my_word, (tile == 0 ? kFlagIncl : kFlagAgg) | tile_count);
+    atomicAdd(reinterpret_cast<u32 *>(glb + (size_t)(tile / kSortGroup) * kRadixBins + tid), (1u << kGroupSumBits) | tile_count);
   }
   // exclusive scans over the digits (other threads contribute zeros)
   const u32 toff = block_exclusive_scan(tile_count, S.warp_sums);
@@ -353,24 +360,29 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
     }
   }
 
-  // ---- decoupled look-back for digit `tid`
+  // ---- decoupled look-back for digit `tid`, two levels
+  // Measured (clock64 per phase): with one word per (tile, digit) the walk went back ~70 tiles
+  // (every in-flight predecessor that has published its count but not yet its prefix) and was
+  // 22-37 % of a CTA's life.  Tiles are therefore also summed per GROUP of kSortGroup
+  // consecutive tiles: each tile adds its count to the group's word with one atomic whose top
+  // bits count arrivals, so a complete group costs one load instead of kSortGroup.  The walk
+  // is: own group's earlier tiles (tile words), then whole groups backwards until a group
+  // that already knows its inclusive prefix.
   if (tid < kRadixBins) {
     u32 prefix = 0;
     if (tile > 0 && live_digit) {
-      // Walk back over the predecessors' words, 8 independent loads per round trip.  Measured
-      // (clock64 per phase): this wait is 22-37 % of a CTA's life; 32 per trip and an early
-      // prefetch were both SLOWER - the walk is bounded by the L2 traffic of 256 digit threads
-      // x ~70 in-flight tiles, not by its latency.  See DESIGN.md §3 for the planned fix.
       constexpr int kLookBatch = 8;
+      const int grp = tile / kSortGroup;
+      const int lo = grp * kSortGroup;
       bool done = false;
-      for (int j = tile - 1; j >= 0 && !done; j -= kLookBatch) {
+      for (int j = tile - 1; j >= lo && !done; j -= kLookBatch) {
         u32 w[kLookBatch];
 #pragma unroll
         for (int q = 0; q < kLookBatch; ++q)
-          w[q] = (j - q >= 0) ? ld_relaxed(my_word - (size_t)(tile - (j - q)) * kRadixBins) : kFlagIncl;
+          w[q] = (j - q >= lo) ? ld_relaxed(my_word - (size_t)(tile - (j - q)) * kRadixBins) : 0u;
 #pragma unroll
         for (int q = 0; q < kLookBatch; ++q) {
-          if (done) break;
+          if (done || j - q < lo) break;
           u32 spins = 0;
           while ((w[q] & kFlagMask) == 0 && ++spins < kSpinLimit)
             w[q] = ld_relaxed(my_word - (size_t)(tile - (j - q)) * kRadixBins);
@@ -379,7 +391,26 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
           if (w[q] & kFlagIncl) done = true;
         }
       }
+      const u64 *gw = glb + tid;
+      for (int g = grp - 1; g >= 0 && !done; g -= kLookBatch) {
+        u64 w[kLookBatch];
+#pragma unroll
+        for (int q = 0; q < kLookBatch; ++q) w[q] = (g - q >= 0) ? ld_relaxed64(gw + (size_t)(g - q) * kRadixBins) : 0ull;
+#pragma unroll
+        for (int q = 0; q < kLookBatch; ++q) {
+          if (done || g - q < 0) break;
+          u32 spins = 0;  // ready: inclusive prefix known (high word) or all kSortGroup tiles have arrived
+          while (!((u32)(w[q] >> 32) & kFlagIncl) && ((u32)w[q] >> kGroupSumBits) != (u32)kSortGroup && ++spins < kSpinLimit)
+            w[q] = ld_relaxed64(gw + (size_t)(g - q) * kRadixBins);
+          const u32 hi = (u32)(w[q] >> 32), low = (u32)w[q];
+          if (hi & kFlagIncl) { prefix += hi & kValMask; done = true; }
+          else if ((low >> kGroupSumBits) == (u32)kSortGroup) prefix += low & ((1u << kGroupSumBits) - 1u);
+          else { atomicOr(&ctl->err, kErrWatchdog); done = true; }
+        }
+      }
       st_relaxed(my_word, kFlagIncl | (prefix + tile_count));
+      if (tile - lo == kSortGroup - 1)  // last tile of its group: the group's inclusive prefix
+        st_relaxed(reinterpret_cast<u32 *>(glb + (size_t)grp * kRadixBins + tid) + 1, kFlagIncl | (prefix + tile_count));
     }
     S.gbase[tid] = digit_base + prefix - toff;
     if (tid == kRadixBins - 1) S.n_valid_tile = toff + tile_count;
