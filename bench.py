@@ -187,11 +187,24 @@ def main():
 
     if world > 1:
         from grid_ndt_b200.tiles import TiledTwoDmap
-        tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local)
+        # two builders deep: the NVLink gather of build i overlaps the SM work of build i+1
+        tmp = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=2)
+        tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=1)  # one at a time (e2e)
         m = tm.map
 
         def step(src):
             tm.build(src, "slope", origin=origin, cuts=None, filter_points=False)
+
+        def run_steps(src, k):
+            n_launch = 0
+            tmp.submit(src, "slope", origin=origin, cuts=None, filter_points=False)
+            for i in range(k):
+                if i + 1 < k:
+                    tmp.submit(src, "slope", origin=origin, cuts=None, filter_points=False)
+                tmp.collect()
+                n_launch += tmp._last.map.launch_count()
+            tmp.join()
+            return n_launch
     else:
         m = TwoDmap(GRID_LEN, Z_LEN, device=local)
         m.setInterval(INTERVAL)
@@ -199,22 +212,26 @@ def main():
         def step(src):
             m.chatterCallback(src, "slope")
 
+        def run_steps(src, k):
+            n_launch = 0
+            for _ in range(k):
+                step(src)
+                n_launch += m.launch_count()
+            return n_launch
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(resident)
+    run_steps(resident, args.warmup)
+    step(resident)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
     with ClockSampler(local) as clk:
         barrier()
         ev0.record()
-        for _ in range(args.steps):
-            step(resident)
-            launches += m.launch_count()
+        launches = run_steps(resident, args.steps)
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)

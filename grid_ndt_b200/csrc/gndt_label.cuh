@@ -158,7 +158,10 @@ struct __align__(128) FinSmem {
   u32 tile;
 };
 
-__global__ void __launch_bounds__(kLabelThreads, 3)
+#ifndef GNDT_FIN_MINBLOCKS
+#define GNDT_FIN_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kLabelThreads, GNDT_FIN_MINBLOCKS)
 finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_slope *slopes,
                       gndt_column *columns, u32 *vfirst, u64 *blk_state, u32 *counters, DevParams P) {
   extern __shared__ __align__(128) unsigned char smem_fin[];

@@ -9,10 +9,16 @@ strip sizes are all-gathered (the only host synchronisation of a build) and ever
 its final records straight out of the builder's table into the other ranks' copy of the whole
 map (batched point-to-point = an all-gather with uneven sizes, no padding, no staging copies;
 measured faster than padded all_gather / broadcasts, tools/gather_bench.py).  Last, strip-local
-column / slope indices are made global by adding per-strip offsets.  torch.distributed is only
-the plumbing (process group, streams, device buffers).
+column / slope indices are made global by adding per-strip offsets.
+
+Back-to-back builds (`depth` > 1): the gather is NVLink work and the build is SM work, so
+`submit()` / `collect()` rotate through `depth` independent builders (handle, stream, halo and
+map buffers each) and the record gather of cloud i runs while cloud i+1 is being built.  The
+halo + size exchange and the record gather use two NCCL communicators so that neither queues
+behind the other.  torch.distributed is only the plumbing (process groups, streams, buffers).
 """
 import ctypes as C
+from collections import deque
 from typing import Optional
 
 import numpy as np
@@ -26,21 +32,53 @@ from .builder import TwoDmap, _check
 REC = VOXEL_DTYPE.itemsize  # 96
 
 
+class _Slot:
+    """One builder with everything a build in flight owns."""
+
+    def __init__(self, res, zres, interval, world, device, halo_records, own_stream):
+        self.map = TwoDmap(res, zres, device=device)
+        self.map.setInterval(interval)
+        self.device = torch.device("cuda", self.map._device)
+        self.stream = torch.cuda.Stream(self.device) if own_stream else None
+        self.counts = torch.zeros(world * 4, dtype=torch.int32, device=self.device)
+        self.halo = torch.zeros(4 * (halo_records + 1) * REC, dtype=torch.uint8, device=self.device)
+        self.table = None
+        self.offsets = None
+        self.strip_counts = None
+
+
 class TiledTwoDmap:
     """Strip r of `world` strips.  `cuts` are contiguous signed x column indices; strip r
     keeps columns with cuts[r] <= cx < cuts[r+1] (gndt_params.tile_lo/hi)."""
 
     def __init__(self, res, zres, interval, rank: int, world: int, device: Optional[int] = None, group=None,
-                 halo_records: int = 32768):
+                 halo_records: int = 32768, depth: int = 1):
         self.rank, self.world, self.group = rank, world, group
-        self.map = TwoDmap(res, zres, device=device)
-        self.map.setInterval(interval)
-        self.device = torch.device("cuda", self.map._device)
-        self._counts = torch.zeros(world * 4, dtype=torch.int32, device=self.device)
-        self._table = None
-        self._halo = None
         self.halo_records = halo_records  # capacity of one halo row (records); overflow is reported, not truncated
-        self.offsets = None
+        self.slots = [_Slot(res, zres, interval, world, device, halo_records, own_stream=depth > 1) for _ in range(depth)]
+        self.gather_group = group
+        if depth > 1 and world > 1:
+            # second communicator: the record gather of build i must not queue behind the halo /
+            # size exchange of build i+1 (collective: every rank constructs its TiledTwoDmap)
+            self.gather_group = dist.new_group(ranks=list(range(world))) if group is None else dist.new_group(
+                ranks=dist.get_process_group_ranks(group))
+        self.map = self.slots[0].map
+        self.device = self.slots[0].device
+        self._next = 0
+        self._inflight = deque()
+        self._last = self.slots[0]
+
+    @property
+    def depth(self) -> int:
+        return len(self.slots)
+
+    @property
+    def offsets(self):
+        return self._last.offsets
+
+    @property
+    def strip_counts(self):
+        return self._last.strip_counts
 
     def plan(self, cloud, origin=None) -> np.ndarray:
         """Balanced cuts from a histogram over x columns.  Every rank that sees the same
@@ -49,100 +87,135 @@ class TiledTwoDmap:
             self.map.setCloudFirst(origin)
         return self.map.plan_tiles(cloud, self.world)
 
-    def build(self, cloud, demand="slope", origin=None, cuts=None, filter_points=True):
-        """Build this rank's strip and assemble the whole map on every rank.  `cloud` may be
-        the whole cloud (filter_points=True: points of other strips are dropped on the
-        device) or only this strip's share.  Returns (table tensor [V_total, 96] uint8 on
-        this rank's GPU, offsets[world+1]).
-
-        Order of work (everything stream-ordered except the one size exchange):
-          1. local build of the strip (no communication: labels are per column)
-          2. thin halo: first / last x row swapped with the two neighbour strips, the strip's
-             own boundary rows get their cross-strip forward/back reachability bits
-          3. strip sizes all-gathered (the only host synchronisation)
-          4. the now-final records go straight from the builder's table into every rank's
-             copy of the map (batched point-to-point = all-gather with uneven sizes)
-          5. strip-local column / slope indices become global (add per-strip offsets)"""
-        m, L = self.map, lib()
+    # ---- phase 1: everything that needs no size on the host ---------------------------------
+    def submit(self, cloud, demand="slope", origin=None, cuts=None, filter_points=True):
+        """Start a build on the next builder (asynchronous): local strip build (labels are per
+        column: no communication), thin halo swapped with the two neighbour strips, own boundary
+        rows finished, strip sizes all-gathered on the device."""
+        if len(self._inflight) == self.depth:
+            raise RuntimeError("all builders busy: collect() before submitting another cloud")
+        s = self.slots[self._next]
+        self._next = (self._next + 1) % self.depth
+        m, L = s.map, lib()
         if origin is not None:
             m.setCloudFirst(origin)
         if cuts is not None and filter_points:
             m.setTile(int(cuts[self.rank]), int(cuts[self.rank + 1]))
         else:
             m.setTile(0, 0)
-        m.uniformDivision(cloud)
-        m.create2DMap(demand)  # (1) asynchronous
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        # (2) halo rows: fixed-size buffers so that no size has to be known on the host
-        slot = (self.halo_records + 1) * REC
-        if self._halo is None:
-            self._halo = torch.zeros(4 * slot, dtype=torch.uint8, device=self.device)
-        send_first, send_last, recv_prev, recv_next = (self._halo[i * slot:(i + 1) * slot] for i in range(4))
-        _check(m._h, L.gndt_halo_pack(m._h, send_first.data_ptr(), send_last.data_ptr(), self.halo_records, st))
-        ops = []
-        if self.rank > 0:
-            ops += [dist.P2POp(dist.isend, send_first, self.rank - 1, group=self.group),
-                    dist.P2POp(dist.irecv, recv_prev, self.rank - 1, group=self.group)]
-        if self.rank + 1 < self.world:
-            ops += [dist.P2POp(dist.isend, send_last, self.rank + 1, group=self.group),
-                    dist.P2POp(dist.irecv, recv_next, self.rank + 1, group=self.group)]
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        _check(m._h, L.gndt_halo_edges(m._h, recv_prev.data_ptr() if self.rank > 0 else None,
-                                       recv_next.data_ptr() if self.rank + 1 < self.world else None, st))
-        # (3) strip sizes: {n_voxels, n_columns, n_slopes, n_fitted} of every strip
-        p_cnt, p_tab, cap = C.c_void_p(), C.c_void_p(), C.c_size_t()
-        _check(m._h, L.gndt_device_count_ptr(m._h, C.byref(p_cnt)))
-        _check(m._h, L.gndt_device_table_ptr(m._h, C.byref(p_tab), C.byref(cap)))
-        mine = _as_tensor(p_cnt.value, 16, self.device).view(torch.int32)
-        dist.all_gather_into_tensor(self._counts, mine, group=self.group)
-        counts4 = self._counts.cpu().numpy().astype(np.int64).reshape(self.world, 4)
-        counts = counts4[:, 0]
-        self.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
-        col_off = np.concatenate([[0], np.cumsum(counts4[:, 1])])[:-1].astype(np.uint32)
-        slope_off = np.concatenate([[0], np.cumsum(counts4[:, 2])])[:-1].astype(np.uint32)
-        total, n = int(self.offsets[-1]), int(counts[self.rank])
-        # (4) records: straight from the builder's table into every rank's map
-        if self._table is None or self._table.numel() < max(total, 1) * REC:
-            self._table = torch.empty(int(max(total, 1) * 1.25) * REC, dtype=torch.uint8, device=self.device)
-        table = self._table
-        local = _as_tensor(p_tab.value, max(n, 1) * REC, self.device)[: n * REC]
-        lo = int(self.offsets[self.rank]) * REC
-        ops = []
-        for r in range(self.world):
-            if r == self.rank or counts[r] == 0:
-                continue
-            ops.append(dist.P2POp(dist.irecv, table[int(self.offsets[r]) * REC: int(self.offsets[r + 1]) * REC], r, group=self.group))
-        if n:
+        stream = s.stream if s.stream is not None else torch.cuda.current_stream(s.device)
+        if s.stream is not None:
+            s.stream.wait_stream(torch.cuda.current_stream(s.device))  # the cloud was produced there
+        with torch.cuda.stream(stream):
+            st = stream.cuda_stream
+            m.uniformDivision(cloud)
+            m.create2DMap(demand, stream=st)
+            slot_b = (self.halo_records + 1) * REC
+            send_first, send_last, recv_prev, recv_next = (s.halo[i * slot_b:(i + 1) * slot_b] for i in range(4))
+            _check(m._h, L.gndt_halo_pack(m._h, send_first.data_ptr(), send_last.data_ptr(), self.halo_records, st))
+            ops = []
+            if self.rank > 0:
+                ops += [dist.P2POp(dist.isend, send_first, self.rank - 1, group=self.group),
+                        dist.P2POp(dist.irecv, recv_prev, self.rank - 1, group=self.group)]
+            if self.rank + 1 < self.world:
+                ops += [dist.P2POp(dist.isend, send_last, self.rank + 1, group=self.group),
+                        dist.P2POp(dist.irecv, recv_next, self.rank + 1, group=self.group)]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            _check(m._h, L.gndt_halo_edges(m._h, recv_prev.data_ptr() if self.rank > 0 else None,
+                                           recv_next.data_ptr() if self.rank + 1 < self.world else None, st))
+            p_cnt = C.c_void_p()
+            _check(m._h, L.gndt_device_count_ptr(m._h, C.byref(p_cnt)))
+            mine = _as_tensor(p_cnt.value, 16, s.device).view(torch.int32)
+            dist.all_gather_into_tensor(s.counts, mine, group=self.group)
+        self._inflight.append(s)
+        return s
+
+    # ---- phase 2: sizes on the host (the one synchronisation), records to every rank ---------
+    def collect(self):
+        """Finish the OLDEST build in flight: returns (table tensor [V_total, 96] uint8 on this
+        rank's GPU, offsets[world+1]).  The gather and the index fix-up are enqueued on the
+        builder's stream; synchronise it (or the device) before reading the table on the host.
+        The table is valid until that builder is used again (`depth` submits later)."""
+        if not self._inflight:
+            raise RuntimeError("nothing submitted")
+        s = self._inflight.popleft()
+        m, L = s.map, lib()
+        stream = s.stream if s.stream is not None else torch.cuda.current_stream(s.device)
+        with torch.cuda.stream(stream):
+            st = stream.cuda_stream
+            counts4 = s.counts.cpu().numpy().astype(np.int64).reshape(self.world, 4)  # {voxels, columns, slopes, fitted}
+            counts = counts4[:, 0]
+            s.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+            col_off = np.concatenate([[0], np.cumsum(counts4[:, 1])])[:-1].astype(np.uint32)
+            slope_off = np.concatenate([[0], np.cumsum(counts4[:, 2])])[:-1].astype(np.uint32)
+            total, n = int(s.offsets[-1]), int(counts[self.rank])
+            if s.table is None or s.table.numel() < max(total, 1) * REC:
+                s.table = torch.empty(int(max(total, 1) * 1.25) * REC, dtype=torch.uint8, device=s.device)
+            table = s.table
+            p_tab, cap = C.c_void_p(), C.c_size_t()
+            _check(m._h, L.gndt_device_table_ptr(m._h, C.byref(p_tab), C.byref(cap)))
+            local = _as_tensor(p_tab.value, max(n, 1) * REC, s.device)[: n * REC]
+            lo = int(s.offsets[self.rank]) * REC
+            ops = []
             for r in range(self.world):
-                if r != self.rank:
-                    ops.append(dist.P2POp(dist.isend, local, r, group=self.group))
-            table[lo: lo + n * REC].copy_(local, non_blocking=True)
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        # (5) global column / slope indices
-        off = (C.c_uint64 * (self.world + 1))(*[int(x) for x in self.offsets])
-        co = (C.c_uint32 * self.world)(*[int(x) for x in col_off])
-        so = (C.c_uint32 * self.world)(*[int(x) for x in slope_off])
-        _check(m._h, L.gndt_apply_strip_offsets(m._h, table.data_ptr(), off, co, so, self.world, st))
-        self.strip_counts = counts4
-        return table[: total * REC].view(-1, REC), self.offsets
+                if r == self.rank or counts[r] == 0:
+                    continue
+                ops.append(dist.P2POp(dist.irecv, table[int(s.offsets[r]) * REC: int(s.offsets[r + 1]) * REC], r,
+                                      group=self.gather_group))
+            if n:
+                for r in range(self.world):
+                    if r != self.rank:
+                        ops.append(dist.P2POp(dist.isend, local, r, group=self.gather_group))
+                table[lo: lo + n * REC].copy_(local, non_blocking=True)
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            off = (C.c_uint64 * (self.world + 1))(*[int(x) for x in s.offsets])
+            co = (C.c_uint32 * self.world)(*[int(x) for x in col_off])
+            so = (C.c_uint32 * self.world)(*[int(x) for x in slope_off])
+            _check(m._h, L.gndt_apply_strip_offsets(m._h, table.data_ptr(), off, co, so, self.world, st))
+        s.strip_counts = counts4
+        self._last = s
+        return table[: total * REC].view(-1, REC), s.offsets
+
+    def build(self, cloud, demand="slope", origin=None, cuts=None, filter_points=True):
+        """One build, start to finish: submit() + collect().  `cloud` may be the whole cloud
+        (filter_points=True: points of other strips are dropped on the device) or only this
+        strip's share."""
+        self.submit(cloud, demand, origin=origin, cuts=cuts, filter_points=filter_points)
+        return self.collect()
+
+    def join(self):
+        """Make the current stream wait for everything enqueued on the builders' streams."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.slots:
+            if s.stream is not None:
+                cur.wait_stream(s.stream)
+
+    def synchronize(self):
+        for s in self.slots:
+            if s.stream is not None:
+                s.stream.synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
 
     def gathered_numpy(self) -> np.ndarray:
-        total = int(self.offsets[-1])
-        return self._table[: total * REC].cpu().numpy().view(VOXEL_DTYPE).reshape(-1)
+        self.synchronize()
+        s = self._last
+        total = int(s.offsets[-1])
+        return s.table[: total * REC].cpu().numpy().view(VOXEL_DTYPE).reshape(-1)
 
     def close(self):
-        self.map.close()
+        for s in self.slots:
+            s.map.close()
 
 
 def allgather_strips(local: torch.Tensor, world: int, group=None):
     """All-gather variable-length strip tables (flat uint8, 96 B records) into one compact
     table in rank order with collectives only (sizes, then padded records).  Device-agnostic:
     NCCL on CUDA tensors, gloo on CPU tensors — the CPU form is what the world_size-2 unit test
-    exercises; TiledTwoDmap.build uses the unpadded point-to-point form of the same exchange.
+    exercises; TiledTwoDmap uses the unpadded point-to-point form of the same exchange.
     Returns (table, offsets)."""
     dev = local.device
     n = local.numel() // REC

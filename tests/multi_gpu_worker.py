@@ -44,8 +44,28 @@ def main():
         assert reach_bad <= 5, f"reach bits differ on {reach_bad} voxels"
         assert sizes.min() > 0.5 * sizes.mean(), f"strips unbalanced: {sizes}"
         print("multi-gpu ok: strips", sizes.tolist(), "reach mismatches", reach_bad)
+    # two builds in flight (depth 2: the gather of the first overlaps the build of the second)
+    # must give the same bytes as one-at-a-time builds
+    cloud_b = synthetic.cfg2(900_000, scale=0.3)
+    dev_b = torch.from_numpy(cloud_b).cuda()
+    origin_b = [float(v) for v in cloud_b[0, :3]]
+    cuts_b = tm.plan(dev_b, origin=origin_b)
+    tm.build(dev_b, "slope", origin=origin_b, cuts=cuts_b, filter_points=True)
+    got_b = tm.gathered_numpy()
+    tm2 = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, depth=2)
+    for rep in range(2):
+        tm2.submit(dev_cloud, "slope", origin=origin, cuts=cuts, filter_points=True)
+        tm2.submit(dev_b, "slope", origin=origin_b, cuts=cuts_b, filter_points=True)
+        ta, _ = tm2.collect()
+        tb, _ = tm2.collect()
+        tm2.synchronize()
+        assert ta.cpu().numpy().tobytes() == got.tobytes(), f"pipelined build A differs (rep {rep})"
+        assert tb.cpu().numpy().tobytes() == got_b.tobytes(), f"pipelined build B differs (rep {rep})"
+    if rank == 0:
+        print("multi-gpu pipelined ok")
     dist.barrier()
     tm.close()
+    tm2.close()
     dist.destroy_process_group()
 
 
