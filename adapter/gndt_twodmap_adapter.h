@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../include/gndt.h"
+#include "../include/gndt_lookup.h"
 
 namespace gndt_adapter {
 
@@ -100,6 +101,39 @@ inline void fill_twodmap(daysun::TwoDmap &m, const float origin[3], const gndt_v
     }
   }
 }
+
+// Integer-keyed view of map_cell for the planner's inner loops:
+// `find` replaces  map_cell.find(quadrant + countMorton(x, y))  (map2D.h:269-272, 396-398;
+// GlobalPlan.h:58-61) and `neighbor` replaces  countLRFB + map_cell.find  (map2D.h:197-263,
+// 539-546) by binary searches over the column table: no string is built or compared.
+// Build it once after fill_twodmap(); it points into `m` and into the caller's column table.
+struct CellIndex {
+  const gndt_column *cols;
+  size_t n_cols;
+  std::vector<daysun::Cell *> cells;  // cells[i] = the Cell of cols[i]
+
+  CellIndex(daysun::TwoDmap &m, const gndt_column *c, size_t n) : cols(c), n_cols(n), cells(n) {
+    for (size_t i = 0; i < n; ++i) {
+      std::map<std::string, daysun::Cell *>::iterator it = m.map_cell.find(morton_key(c[i].sx, c[i].sy));
+      cells[i] = it == m.map_cell.end() ? NULL : it->second;
+    }
+  }
+  daysun::Cell *find(int sx, int sy) const {
+    const int64_t i = gndtl_find_column(cols, n_cols, sx, sy);
+    return i < 0 ? NULL : cells[(size_t)i];
+  }
+  // dir: 0 left, 1 right, 2 forward, 3 back (leftMtn / rightMtn / forMtn / backMtn of countLRFB)
+  daysun::Cell *neighbor(int sx, int sy, int dir) const {
+    const int64_t i = gndtl_neighbor_column(cols, n_cols, sx, sy, dir);
+    return i < 0 ? NULL : cells[(size_t)i];
+  }
+  daysun::Slope *find_slope(int sx, int sy, int sz) const {
+    daysun::Cell *c = find(sx, sy);
+    if (!c) return NULL;
+    std::map<int, daysun::Slope *, CmpByKeyUD>::iterator it = c->map_slope.find(sz);
+    return it == c->map_slope.end() ? NULL : it->second;
+  }
+};
 
 }  // namespace gndt_adapter
 #endif

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("GNDT_LIB") or os.path.join(HERE, "libgndt.so")  # GND
 SOURCES = [os.path.join(HERE, "csrc", f) for f in (
     "gndt_api.cu", "gndt_device.cuh", "gndt_sort.cuh", "gndt_reduce.cuh", "gndt_label.cuh", "gndt_update.cuh")]
 HEADER = os.path.join(REPO, "include", "gndt.h")
+LOOKUP_HEADER = os.path.join(REPO, "include", "gndt_lookup.h")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -20,7 +21,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 
 def build_library(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> grid_ndt_b200/libgndt.so (in-tree)."""
-    deps = SOURCES + [HEADER]
+    deps = SOURCES + [HEADER, LOOKUP_HEADER]
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
         return LIB_PATH
@@ -75,6 +76,9 @@ SYMBOLS = {
     "gndt_cell_center": (_i, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32,
                               C.POINTER(C.c_float)]),
     "gndt_origin": (_i, [_vp, C.POINTER(C.c_float)]),
+    "gndt_find_column": (C.c_int64, [_vp, _sz, C.c_int32, C.c_int32]),
+    "gndt_find_slope": (C.c_int64, [_vp, _sz, _vp, C.c_int32, C.c_int32, C.c_int32]),
+    "gndt_neighbor_column": (C.c_int64, [_vp, _sz, C.c_int32, C.c_int32, _i]),
 }
 
 

@@ -271,6 +271,25 @@ class TwoDmap:
             raise GndtError(rc, "position outside the supported index range")
         return morton_string(sx.value, sy.value), sz.value
 
+    # ---- integer-keyed lookups (what the planner does with strings) ----
+    def find_column(self, sx: int, sy: int) -> int:
+        """Index of cell (sx, sy) in `columns`, -1 if empty: map_cell.find(morton_xy) of
+        map2D.h:269-272 without building the key string."""
+        c = self.columns
+        return int(lib().gndt_find_column(c.ctypes.data, len(c), int(sx), int(sy)))
+
+    def find_slope(self, sx: int, sy: int, sz: int) -> int:
+        """Index into `slopes` of the Slope at layer sz of cell (sx, sy), -1 if none:
+        map_cell[xy]->map_slope.find(z) (GlobalPlan.h:58-61)."""
+        c, s = self.columns, self.slopes
+        return int(lib().gndt_find_slope(c.ctypes.data, len(c), s.ctypes.data, int(sx), int(sy), int(sz)))
+
+    def neighbor_column(self, sx: int, sy: int, direction: int) -> int:
+        """Index of the left/right/forward/back (0..3) neighbour cell of countLRFB
+        (map2D.h:197-263), -1 if that cell is empty."""
+        c = self.columns
+        return int(lib().gndt_neighbor_column(c.ctypes.data, len(c), int(sx), int(sy), int(direction)))
+
     # ---- the reference's public containers, rebuilt lazily on the host -------------------
     @property
     def morton_list(self):

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "gndt_device.cuh"
+#include "gndt_lookup.h"
 #include "gndt_label.cuh"
 #include "gndt_reduce.cuh"
 #include "gndt_sort.cuh"
@@ -829,6 +830,17 @@ int gndt_cell_center(const float origin[3], float grid_len, float z_len, int32_t
   center[1] = (float)(sy > 0 ? ay + origin[1] : origin[1] - ay);
   center[2] = (float)(sz > 0 ? origin[2] + az : origin[2] - az);
   return GNDT_OK;
+}
+
+int64_t gndt_find_column(const gndt_column *cols, size_t n_cols, int32_t sx, int32_t sy) {
+  return gndtl_find_column(cols, n_cols, sx, sy);
+}
+int64_t gndt_find_slope(const gndt_column *cols, size_t n_cols, const gndt_slope *slopes, int32_t sx, int32_t sy,
+                        int32_t sz) {
+  return gndtl_find_slope(cols, n_cols, slopes, sx, sy, sz);
+}
+int64_t gndt_neighbor_column(const gndt_column *cols, size_t n_cols, int32_t sx, int32_t sy, int dir) {
+  return gndtl_neighbor_column(cols, n_cols, sx, sy, dir);
 }
 
 int gndt_origin(gndt_handle *h, float origin[3]) {

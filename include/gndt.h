@@ -280,6 +280,16 @@ int gndt_morton_string(int32_t sx, int32_t sy, char *buf);
 /* TwoDmap::countPositionXYZ (include/map2D.h:918-947): centre of cell (sx,sy,sz), metres. */
 int gndt_cell_center(const float origin[3], float grid_len, float z_len, int32_t sx, int32_t sy,
                      int32_t sz, float center[3]);
+/* Integer-keyed replacements for the planner's string lookups `map_cell.find(morton_xy)` /
+ * `map_slope.find(morton_z)` (include/map2D.h:269-272,396-398; include/GlobalPlan.h:58-61) and
+ * for the neighbour keys of countLRFB (include/map2D.h:197-263), on the caller's copies of the
+ * column / slope tables: binary searches, no strings (inline
+ * forms in include/gndt_lookup.h).  Return the table index or -1.  dir: 0 left, 1 right,
+ * 2 forward, 3 back, as in GNDT_F_REACH_L/R/F/B. */
+int64_t gndt_find_column(const gndt_column *cols, size_t n_cols, int32_t sx, int32_t sy);
+int64_t gndt_find_slope(const gndt_column *cols, size_t n_cols, const gndt_slope *slopes, int32_t sx, int32_t sy,
+                        int32_t sz);
+int64_t gndt_neighbor_column(const gndt_column *cols, size_t n_cols, int32_t sx, int32_t sy, int dir);
 /* The map origin in use (TwoDmap::cloudFirst, map2D.h:193,490-492): point 0 of the initial
  * cloud when origin_is_first_point, else params.origin. */
 int gndt_origin(gndt_handle *h, float origin[3]);

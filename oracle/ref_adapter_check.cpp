@@ -3,6 +3,7 @@
 // the map the reference itself built in the last gndt_ref_build call (global `map2D` of
 // src/receiver.cpp).  Part of the same translation unit as ref_driver.cpp (the reference
 // headers have no include guards for their function definitions).
+#include <time.h>
 #include "../adapter/gndt_twodmap_adapter.h"
 
 extern "C" int gndt_ref_adapter_check(const float *origin, const gndt_params *P, const gndt_voxel *vox, size_t nv,
@@ -45,5 +46,74 @@ extern "C" int gndt_ref_adapter_check(const float *origin, const gndt_params *P,
   std::string key2; int z2;
   map2D.transMortonXYZ(octomath::Vector3(origin[0] + 1.234f, origin[1] - 0.77f, origin[2]), key2, z2);
   if (key != key2 || z != z2) bad += 1000;
+  return bad;
+}
+
+// ---- integer-keyed lookups (adapter CellIndex / include/gndt_lookup.h) against the reference's
+// own string path: map_cell.find(key) for every cell and a ring of empty cells around it, and
+// the four neighbour keys produced by the reference's private TwoDmap::countLRFB (reached
+// through an explicit-instantiation accessor: access control is not checked there).
+namespace {
+typedef void (daysun::TwoDmap::*LrfbFn)(std::string, int, int, std::string &, std::string &, std::string &, std::string &);
+template <typename Tag, LrfbFn M> struct PrivateAccess { friend LrfbFn gndt_get(Tag) { return M; } };
+struct LrfbTag { friend LrfbFn gndt_get(LrfbTag); };
+template struct PrivateAccess<LrfbTag, &daysun::TwoDmap::countLRFB>;
+double now_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+}  // namespace
+
+// Returns the number of mismatches; rates[0] = string lookups/s, rates[1] = integer lookups/s
+// over the same sequence of neighbour queries (4 per cell).
+extern "C" int gndt_ref_lookup_check(const float *origin, const gndt_params *P, const gndt_voxel *vox, size_t nv,
+                                     const gndt_slope *sl, size_t ns, const gndt_column *cols, size_t nc, double *rates) {
+  daysun::TwoDmap m(P->grid_len, P->z_len);
+  m.setInterval(P->slope_interval);
+  gndt_adapter::fill_twodmap(m, origin, vox, nv, sl, ns, cols, nc, false);
+  gndt_adapter::CellIndex index(m, cols, nc);
+  const LrfbFn lrfb = gndt_get(LrfbTag());
+  int bad = 0;
+  for (size_t i = 0; i < nc; ++i) {
+    const int sx = cols[i].sx, sy = cols[i].sy;
+    std::map<std::string, Cell *>::iterator it = m.map_cell.find(gndt_adapter::morton_key(sx, sy));
+    if (it == m.map_cell.end() || index.find(sx, sy) != it->second) ++bad;
+    for (int dx = -2; dx <= 2; ++dx)
+      for (int dy = -2; dy <= 2; ++dy) {  // present and absent cells around it (skipping index 0)
+        const int tx = sx + dx, ty = sy + dy;
+        if (tx == 0 || ty == 0) { if (index.find(tx, ty) != NULL) ++bad; continue; }
+        std::map<std::string, Cell *>::iterator jt = m.map_cell.find(gndt_adapter::morton_key(tx, ty));
+        if (index.find(tx, ty) != (jt == m.map_cell.end() ? (Cell *)NULL : jt->second)) ++bad;
+      }
+    const std::string q(1, sx > 0 ? (sy > 0 ? 'A' : 'B') : (sy > 0 ? 'C' : 'D'));
+    std::string k[4];
+    (m.*lrfb)(q, std::abs(sx), std::abs(sy), k[0], k[1], k[2], k[3]);
+    for (int d = 0; d < 4; ++d) {
+      std::map<std::string, Cell *>::iterator jt = m.map_cell.find(k[d]);
+      if (index.neighbor(sx, sy, d) != (jt == m.map_cell.end() ? (Cell *)NULL : jt->second)) ++bad;
+    }
+    // slopes of the cell: map_slope.find(z) for every layer present and one absent
+    for (unsigned s = cols[i].slope_begin; s < cols[i].slope_begin + cols[i].slope_count; ++s) {
+      if (gndtl_find_slope(cols, nc, sl, sx, sy, sl[s].sz) != (int64_t)s) ++bad;
+      if (index.find_slope(sx, sy, sl[s].sz) == NULL) ++bad;
+    }
+    if (gndtl_find_slope(cols, nc, sl, sx, sy, 32760) != -1) ++bad;
+  }
+  if (rates) {  // the planner's inner loop: 4 neighbour cells per expansion
+    size_t hits = 0;
+    double t0 = now_s();
+    for (size_t i = 0; i < nc; ++i) {
+      const int sx = cols[i].sx, sy = cols[i].sy;
+      const std::string q(1, sx > 0 ? (sy > 0 ? 'A' : 'B') : (sy > 0 ? 'C' : 'D'));
+      std::string k[4];
+      (m.*lrfb)(q, std::abs(sx), std::abs(sy), k[0], k[1], k[2], k[3]);
+      for (int d = 0; d < 4; ++d) hits += m.map_cell.find(k[d]) != m.map_cell.end();
+    }
+    double t1 = now_s();
+    size_t hits2 = 0;
+    for (size_t i = 0; i < nc; ++i)
+      for (int d = 0; d < 4; ++d) hits2 += index.neighbor(cols[i].sx, cols[i].sy, d) != NULL;
+    double t2 = now_s();
+    if (hits != hits2) ++bad;
+    rates[0] = 4.0 * nc / (t1 - t0);
+    rates[1] = 4.0 * nc / (t2 - t1);
+  }
   return bad;
 }

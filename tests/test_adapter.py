@@ -39,3 +39,27 @@ def test_adapter_rebuilds_reference_containers(name, n, gl, kw, demand):
     origin = np.ascontiguousarray(cloud[0, :3], np.float32)
     bad = fn(origin.ctypes.data, C.byref(p), vox.ctypes.data, len(vox), sl.ctypes.data, len(sl), cols.ctypes.data, len(cols), 1)
     assert bad == 0, f"adapter mismatch code {bad}"
+
+
+@pytest.mark.parametrize("name,n,gl,kw", [("cfg1", 60_000, 0.2, {}), ("cfg2", 150_000, 0.2, {"scale": 0.15})])
+def test_integer_lookups_equal_reference_string_lookups(name, n, gl, kw):
+    """adapter CellIndex / include/gndt_lookup.h against map_cell.find(key) and the neighbour
+    keys of the reference's own (private) TwoDmap::countLRFB, for every cell, a ring of empty
+    cells around each, and all four directions."""
+    cloud = synthetic.make(name, n, **kw)
+    p = default_params(gl, 0.1, 0.08, "slope")
+    o = O.oracle_build(cloud, p)
+    vox, cols, sl = o.voxels, o.columns, slopes_of(o.voxels)
+    # the port's slope table is compacted like the library's: slope_begin/count index into it
+    lib = O._lib("ref")
+    fn = lib.gndt_ref_lookup_check
+    fn.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                   C.POINTER(C.c_double)]
+    fn.restype = C.c_int
+    origin = np.ascontiguousarray(cloud[0, :3], np.float32)
+    rates = (C.c_double * 2)()
+    bad = fn(origin.ctypes.data, C.byref(p), vox.ctypes.data, len(vox), sl.ctypes.data, len(sl), cols.ctypes.data, len(cols), rates)
+    assert bad == 0, f"{bad} lookups differ between the integer tables and the reference's string maps"
+    print(f"\n{name}: {len(cols)} cells; neighbour lookups/s: reference strings {rates[0]:.3g}, integer tables {rates[1]:.3g} "
+          f"({rates[1] / rates[0]:.0f}x)")
+    assert rates[1] > rates[0]

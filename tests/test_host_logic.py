@@ -118,3 +118,44 @@ def test_bench_reference_arm_nonzero_rank_is_silent():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"], env=env, timeout=120)
     assert out.strip() == b""
+
+
+def test_integer_lookups_on_oracle_tables():
+    """gndt_find_column / gndt_find_slope / gndt_neighbor_column (host helpers of libgndt.so, no
+    GPU involved) on tables produced by the oracle: every cell is found at its own index, empty
+    cells and index 0 give -1, neighbours are one step in contiguous index space with the
+    quadrant crossing between -1 and +1 (countLRFB, map2D.h:197-263)."""
+    import ctypes as C
+    import numpy as np
+    from grid_ndt_b200 import lib, synthetic
+    from grid_ndt_b200._abi import SLOPE_DTYPE, default_params
+    from oracle import oracle as O
+    cloud = synthetic.cfg2(120_000, scale=0.12)
+    cloud[:, :2] -= cloud[0, :2] * np.float32(0.5)  # all four quadrants around the first point
+    cloud[0, :2] = cloud[1:, :2].mean(axis=0)
+    o = O.oracle_build(cloud, default_params(0.2, 0.1, 0.08))
+    cols, vox = o.columns, o.voxels
+    assert len({(int(np.sign(c["sx"])), int(np.sign(c["sy"]))) for c in cols}) == 4, "want all four quadrants"
+    idx = np.nonzero(vox["flags"] & 2)[0]
+    sl = np.zeros(len(idx), SLOPE_DTYPE)
+    for f in ("sx", "sy", "sz"):
+        sl[f] = vox[f][idx]
+    L = lib()
+    table = {(int(c["sx"]), int(c["sy"])): i for i, c in enumerate(cols)}
+    cont = lambda s: s - 1 if s > 0 else s
+    sgn = lambda c: c + 1 if c >= 0 else c
+    step = {0: (0, -1), 1: (0, 1), 2: (1, 0), 3: (-1, 0)}
+    rng = np.random.default_rng(5)
+    for i in rng.choice(len(cols), 3000, replace=False):
+        sx, sy = int(cols[i]["sx"]), int(cols[i]["sy"])
+        assert L.gndt_find_column(cols.ctypes.data, len(cols), sx, sy) == i
+        for d, (dx, dy) in step.items():
+            want = table.get((sgn(cont(sx) + dx), sgn(cont(sy) + dy)), -1)
+            assert L.gndt_neighbor_column(cols.ctypes.data, len(cols), sx, sy, d) == want
+        for s in range(cols[i]["slope_begin"], cols[i]["slope_begin"] + cols[i]["slope_count"]):
+            assert L.gndt_find_slope(cols.ctypes.data, len(cols), sl.ctypes.data, sx, sy, int(sl[s]["sz"])) == s
+        assert L.gndt_find_slope(cols.ctypes.data, len(cols), sl.ctypes.data, sx, sy, 32000) == -1
+    assert L.gndt_find_column(cols.ctypes.data, len(cols), 0, 5) == -1
+    assert L.gndt_find_column(cols.ctypes.data, len(cols), 30000, 30000) == -1
+    assert L.gndt_neighbor_column(cols.ctypes.data, len(cols), 1, 1, 7) == -1
+    assert L.gndt_find_column(None, 0, 1, 1) == -1
