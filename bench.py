@@ -15,7 +15,8 @@ the finished strips gathered over NCCL inside the timed region.
             host->device copy of the cloud and the device->host copy of the voxel / slope /
             column tables inside the timed region, every step.  At N = 1 the headline e2e
             runs two builders deep (CloudPipeline: upload of cloud i+1 overlaps build and
-            read-back of cloud i); the one-at-a-time figure is `serial_ms_per_step`.
+            read-back of cloud i), at N > 1 the two-deep strip pipeline with host input;
+            the one-at-a-time figure is `serial_ms_per_step`.
 `roofline`: algorithmic bytes of one build (16 B per point read once + 96 B per voxel
             record written once) / device time per build, against the
             measured HBM copy bandwidth in MEASURED_PEAKS.json.
@@ -37,7 +38,7 @@ CFG = "cfg2"
 POINTS_PER_GPU = 10_000_000
 GRID_LEN, Z_LEN, INTERVAL = 0.2, 0.1, 0.08
 SCENE_W = 120.0
-REF_STEP_POINTS = 2_000_000      # --impl reference: points per timed step (bounded sample)
+REF_STEP_POINTS = 1_000_000      # --impl reference: points per timed step (bounded sample; smaller samples flatter the CPU code)
 CPU_BASELINE_POINTS = 4_000_000  # cpu_baseline leg of the default run
 
 
@@ -149,7 +150,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.json_out.write(json.dumps(line) + "\n")
+    args.json_out.flush()
     return 0
 
 
@@ -162,6 +164,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON: everything else any library writes to fd 1
+    # (NCCL's version banner, for one) is sent to stderr for the whole run
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    args.json_out = json_out
     if args.impl == "reference":
         return run_reference(args)
 
@@ -177,8 +185,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cloud = make_cloud(rank)
@@ -291,6 +297,25 @@ def main():
         e2e_s = wall(piped, n_e2e)
         e2e_mode = "CloudPipeline depth 2: H2D of cloud i+1 overlaps kernels + D2H of cloud i"
         pipe.close()
+    else:
+        # N > 1: the two-deep strip pipeline with HOST input: upload of cloud i+1 overlaps the
+        # gather and the read-back of this rank's strip tables of cloud i
+        for sl in tmp.slots:
+            sl.map.pin_results(True)
+
+        def piped(n):
+            tmp.submit(host, "slope", origin=origin, cuts=None, filter_points=False)
+            for i in range(n):
+                if i + 1 < n:
+                    tmp.submit(host, "slope", origin=origin, cuts=None, filter_points=False)
+                tmp.collect()
+                mm = tmp._last.map
+                got = mm.voxels.nbytes + mm.slopes.nbytes + mm.columns.nbytes
+                assert got == d2h, (got, d2h)
+            tmp.synchronize()
+        piped(3)
+        e2e_s = wall(piped, n_e2e)
+        e2e_mode = "TiledTwoDmap depth 2, host input: H2D of cloud i+1 overlaps NCCL gather + D2H of cloud i"
     e2e_value = total_pts / e2e_s
 
     peak, peak_src = measured_peak()
@@ -339,7 +364,8 @@ def main():
                                           f"(division {r.division_s:.1f} s + calculate {r.calculate_s:.1f} s); single thread like the reference's initial-build loop",
                                 "host_cores_available": os.cpu_count()}
     if rank == 0:
-        print(json.dumps(line))
+        args.json_out.write(json.dumps(line) + "\n")
+        args.json_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
