@@ -340,14 +340,16 @@ __global__ void column_finish_kernel(Ctl *ctl, const gndt_voxel *table, const u3
 // dot product, binary64 norms (pow(float,int) -> double), quotient stored to float,
 // acos(float), degrees via *180 (float) then /M_PI (double) stored to float, folded to
 // <= 90.  res > 1 gives NaN, which fails the <= test exactly like the reference.
-__device__ __forceinline__ float count_angle(const float a[3], const float b[3]) {
+__device__ __forceinline__ double normal_length(const float a[3]) {
+  return sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)a[0], (double)a[0]), __dmul_rn((double)a[1], (double)a[1])),
+                        __dmul_rn((double)a[2], (double)a[2])));
+}
+// l2 = normal_length(b): the same value for every neighbour of one Slope, computed once.
+__device__ __forceinline__ float count_angle(const float a[3], const float b[3], double l2) {
   float dot = __fmul_rn(a[0], b[0]);
   dot = __fadd_rn(dot, __fmul_rn(a[1], b[1]));
   dot = __fadd_rn(dot, __fmul_rn(a[2], b[2]));
-  const double l1 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)a[0], (double)a[0]), __dmul_rn((double)a[1], (double)a[1])),
-                                   __dmul_rn((double)a[2], (double)a[2])));
-  const double l2 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)b[0], (double)b[0]), __dmul_rn((double)b[1], (double)b[1])),
-                                   __dmul_rn((double)b[2], (double)b[2])));
+  const double l1 = normal_length(a);
   const float res = (float)((double)dot / __dmul_rn(l1, l2));
   const float deg = __fmul_rn(acosf(res), 180.f);
   float an = (float)((double)deg / 3.14159265358979323846);
@@ -357,15 +359,17 @@ __device__ __forceinline__ float count_angle(const float a[3], const float b[3])
 
 // Does neighbour cell `c` hold a Slope reachable from (normal n, mean z)?  countReachable's
 // four tests (map2D.h:276-279 / 284-287; thresholds robot.h:38-46).
+// The four tests are a pure conjunction, so the cheap ones run first and the angle (two
+// binary64 divisions, a square root and acosf) only for candidates that pass them.
 __device__ __forceinline__ bool cell_reachable(const gndt_column &c, const gndt_slope *slopes, const float n[3],
-                                               float mz, const DevParams &P) {
+                                               double n_len, float mz, const DevParams &P) {
   for (u32 s = c.slope_begin; s < c.slope_begin + c.slope_count; ++s) {
     const gndt_slope &t = slopes[s];
     if (t.flags & GNDT_F_UP) continue;
     if (!(t.rough <= P.rough_max)) continue;
-    const float tn[3] = {t.normal[0], t.normal[1], t.normal[2]};
-    if (!(count_angle(tn, n) <= P.angle_max_deg)) continue;
     if (!(fabsf(__fsub_rn(t.mean[2], mz)) <= P.reach_height)) continue;
+    const float tn[3] = {t.normal[0], t.normal[1], t.normal[2]};
+    if (!(count_angle(tn, n, n_len) <= P.angle_max_deg)) continue;
     return true;
   }
   return false;
@@ -394,29 +398,54 @@ edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column 
     }
     const u32 ci = table[me.voxel].column;
     const float n[3] = {me.normal[0], me.normal[1], me.normal[2]};
+    const double n_len = normal_length(n);
     u32 bits = 0;
     if (ci > 0) {  // left: cy-1
       const gndt_column c = columns[ci - 1];
-      if (contiguous_index(c.sx) == cx && contiguous_index(c.sy) == cy - 1 && cell_reachable(c, slopes, n, me.mean[2], P))
+      if (contiguous_index(c.sx) == cx && contiguous_index(c.sy) == cy - 1 && cell_reachable(c, slopes, n, n_len, me.mean[2], P))
         bits |= GNDT_F_REACH_L;
     }
     if (ci + 1 < C) {  // right: cy+1
       const gndt_column c = columns[ci + 1];
-      if (contiguous_index(c.sx) == cx && contiguous_index(c.sy) == cy + 1 && cell_reachable(c, slopes, n, me.mean[2], P))
+      if (contiguous_index(c.sx) == cx && contiguous_index(c.sy) == cy + 1 && cell_reachable(c, slopes, n, n_len, me.mean[2], P))
         bits |= GNDT_F_REACH_R;
     }
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {  // forward: cx+1, back: cx-1
       const int ncx = cx + (dir == 0 ? 1 : -1);
       if (ncx < cx_base || ncx > cx_max) continue;
-      u32 lo = row_start[ncx - cx_base], hi = row_end[ncx - cx_base];
-      while (lo < hi) {  // first column of the row with cy' >= cy
+      // first column of the neighbour row with cy' >= cy.  Neighbouring rows of a map are
+      // populated alike, so the same offset as in the own row is a good first guess; gallop
+      // from it to bracket cy, then bisect the bracket (1-3 probes instead of log2(row)).
+      const u32 r_lo = row_start[ncx - cx_base], r_hi = row_end[ncx - cx_base];
+      u32 lo = r_lo, hi = r_hi;
+      if (r_lo < r_hi) {
+        const u32 g = r_lo + min(ci - row_start[cx - cx_base], r_hi - r_lo - 1u);
+        if (contiguous_index(columns[g].sy) < cy) {
+          lo = g + 1;
+          for (u32 step = 1;; step <<= 1) {
+            const u32 probe = lo + step - 1;
+            if (probe >= r_hi) { hi = r_hi; break; }
+            if (contiguous_index(columns[probe].sy) >= cy) { hi = probe; break; }
+            lo = probe + 1;
+          }
+        } else {
+          hi = g;
+          for (u32 step = 1;; step <<= 1) {
+            if (hi < r_lo + step) { lo = r_lo; break; }
+            const u32 probe = hi - step;
+            if (contiguous_index(columns[probe].sy) < cy) { lo = probe + 1; break; }
+            hi = probe;
+          }
+        }
+      }
+      while (lo < hi) {
         const u32 mid = (lo + hi) >> 1;
         if (contiguous_index(columns[mid].sy) < cy) lo = mid + 1; else hi = mid;
       }
       if (lo < row_end[ncx - cx_base]) {
         const gndt_column c = columns[lo];
-        if (contiguous_index(c.sy) == cy && cell_reachable(c, slopes, n, me.mean[2], P))
+        if (contiguous_index(c.sy) == cy && cell_reachable(c, slopes, n, n_len, me.mean[2], P))
           bits |= (dir == 0 ? GNDT_F_REACH_F : GNDT_F_REACH_B);
       }
     }
@@ -491,9 +520,9 @@ __device__ __forceinline__ bool halo_reachable(const gndt_voxel *halo, u32 n_hal
     const gndt_voxel &t = halo[v];
     if (!(t.flags & GNDT_F_SLOPE) || (t.flags & GNDT_F_UP)) continue;
     if (!(t.rough <= P.rough_max)) continue;
-    const float tn[3] = {t.normal[0], t.normal[1], t.normal[2]};
-    if (!(count_angle(tn, n) <= P.angle_max_deg)) continue;
     if (!(fabsf(__fsub_rn(t.mean[2], mz)) <= P.reach_height)) continue;
+    const float tn[3] = {t.normal[0], t.normal[1], t.normal[2]};
+    if (!(count_angle(tn, n, normal_length(n)) <= P.angle_max_deg)) continue;
     return true;
   }
   return false;
