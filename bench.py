@@ -215,7 +215,7 @@ def main():
                     tmp.submit(src, "slope", origin=origin, cuts=None, filter_points=False)
                     ahead += 1
                 tmp.collect()
-                n_launch += tmp._last.map.launch_count()
+                n_launch += tmp.last_map.launch_count()
             tmp.join()
             return n_launch
     else:
@@ -232,10 +232,10 @@ def main():
         def run_steps(src, k):
             n_launch = 0
             for _ in range(k):
-                if len(flight._inflight) == flight.depth:
+                if flight.pending == flight.depth:
                     n_launch += flight.release().launch_count()
                 flight.submit(src)
-            while flight._inflight:
+            while flight.pending:
                 n_launch += flight.release().launch_count()
             flight.join()
             return n_launch
@@ -332,7 +332,7 @@ def main():
                 if i + 1 < n:
                     tmp.submit(host, "slope", origin=origin, cuts=None, filter_points=False)
                 tmp.collect()
-                mm = tmp._last.map
+                mm = tmp.last_map
                 got = mm.voxels.nbytes + mm.slopes.nbytes + mm.columns.nbytes
                 assert got == d2h, (got, d2h)
             tmp.synchronize()

@@ -41,6 +41,11 @@ class CloudPipeline:
     def depth(self) -> int:
         return len(self.maps)
 
+    @property
+    def pending(self) -> int:
+        """Builds submitted and not yet collected / released."""
+        return len(self._inflight)
+
     def submit(self, cloud, origin=None) -> int:
         """Start one build (asynchronous).  `cloud`: float32 [n, >=3], a pinned host tensor for the
         overlap to happen (pageable memory works but the copy then blocks the caller).  The

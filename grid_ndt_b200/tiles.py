@@ -73,6 +73,17 @@ class TiledTwoDmap:
         return len(self.slots)
 
     @property
+    def pending(self) -> int:
+        """Builds submitted and not yet collected."""
+        return len(self._inflight)
+
+    @property
+    def last_map(self) -> TwoDmap:
+        """The builder of the build most recently collected (its strip-local tables, counts,
+        stage times)."""
+        return self._last.map
+
+    @property
     def offsets(self):
         return self._last.offsets
 
