@@ -27,6 +27,11 @@ namespace gndt {
 #ifndef GNDT_SORT_MINBLOCKS
 #define GNDT_SORT_MINBLOCKS 3
 #endif
+#ifdef GNDT_SORT_WHIST16
+typedef unsigned short whist_t;
+#else
+typedef u32 whist_t;
+#endif
 constexpr int kSortThreads = GNDT_SORT_THREADS;
 constexpr int kSortItems = GNDT_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 3072 points = 48 KB staged
@@ -43,7 +48,7 @@ struct __align__(128) SortSmem {
   float4 in[kSortTile];            // the tile, in arrival order (TMA destination)
   u32 slot[kSortTile];             // digit << 16 | source position, in digit order; pass 0 first
                                    // uses this space for the histograms of the later digits
-  u32 whist[kSortWarps][kRadixBins];
+  whist_t whist[kSortWarps][kRadixBins];  // per-warp digit counts (<= 32 * kSortItems each)
   u32 tile_off[kRadixBins];
   u32 gbase[kRadixBins];
   u32 warp_sums[16];
@@ -312,7 +317,7 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
     u32 old = 0;
     if (lane == leader && dg[k] != kInvalidDigit) {
       old = S.whist[warp][dg[k]];
-      S.whist[warp][dg[k]] = old + __popc(peers);
+      S.whist[warp][dg[k]] = (whist_t)(old + __popc(peers));
     }
     old = __shfl_sync(0xffffffffu, old, leader);
     rank[k] = old + r;
@@ -339,7 +344,7 @@ sort_pass_kernel(Ctl *ctl, int pass, const float *in_raw, size_t stride_f, size_
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       const u32 t = S.whist[w][tid];
-      S.whist[w][tid] = tile_count;
+      S.whist[w][tid] = (whist_t)tile_count;
       tile_count += t;
     }
     st_relaxed(my_word, (tile == 0 ? kFlagIncl : kFlagAgg) | tile_count);
