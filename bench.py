@@ -355,6 +355,15 @@ def main():
         except Exception:
             traffic = None
 
+    layout = m.key_layout()
+    n_pass = max(1, layout["passes"])
+    pass_ms = stages["sort"] / n_pass
+    pass_bytes = 32.0 * n_pts  # every point read once and written once per pass
+    dominant = {"name": "sort_pass_kernel", "launches_per_build": n_pass, "share_of_build": stages["sort"] / stages["total"],
+                "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_ms,
+                "achieved": pass_bytes / (pass_ms * 1e-3) / 1e9, "frac": pass_bytes / (pass_ms * 1e-3) / 1e9 / peak,
+                "note": "the same memory pattern with no other work runs at 4.9 TB/s (tools/micro/scatter_pattern.cu, 65 us)"}
+
     line = {
         "metric": "ndt_map_build_points_per_sec", "value": value, "unit": "points/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -368,6 +377,7 @@ def main():
         "stage_ms": stages,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes": b_alg, "kernel_ms": t_build_ms,
+                     "dominant_kernel": dominant,
                      "achieved_in_flight": (b_alg / (ms_per_step * 1e-3) / 1e9) if world == 1 else None,
                      "what": "whole build (all kernels of one step) on one GPU, one build at a time: (16 B x points + 96 B x voxels) / "
                              "device time of the build (stage events); achieved_in_flight = the same bytes / ms_per_step of the timed "

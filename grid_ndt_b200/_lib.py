@@ -76,6 +76,7 @@ SYMBOLS = {
     "gndt_cell_center": (_i, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32,
                               C.POINTER(C.c_float)]),
     "gndt_origin": (_i, [_vp, C.POINTER(C.c_float)]),
+    "gndt_key_layout": (_i, [_vp, C.POINTER(C.c_int)]),
     "gndt_find_column": (C.c_int64, [_vp, _sz, C.c_int32, C.c_int32]),
     "gndt_find_slope": (C.c_int64, [_vp, _sz, _vp, C.c_int32, C.c_int32, C.c_int32]),
     "gndt_neighbor_column": (C.c_int64, [_vp, _sz, C.c_int32, C.c_int32, _i]),

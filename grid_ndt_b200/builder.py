@@ -239,6 +239,12 @@ class TwoDmap:
         _check(self._h, lib().gndt_fast_div_status(self._h, C.byref(en), C.byref(n)))
         return bool(en.value), int(n.value)
 
+    def key_layout(self) -> dict:
+        """Live partition passes and key-field widths of the last build (introspection)."""
+        out = (C.c_int * 4)()
+        _check(self._h, lib().gndt_key_layout(self._h, out))
+        return {"passes": out[0], "bits_x": out[1], "bits_y": out[2], "bits_z": out[3]}
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         _check(self._h, lib().gndt_launch_count(self._h, C.byref(n)))

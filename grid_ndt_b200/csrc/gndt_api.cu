@@ -832,6 +832,14 @@ int gndt_cell_center(const float origin[3], float grid_len, float z_len, int32_t
   return GNDT_OK;
 }
 
+int gndt_key_layout(gndt_handle *h, int out[4]) {
+  if (!h || !out) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  out[0] = h->host_ctl.n_passes; out[1] = h->host_ctl.bx; out[2] = h->host_ctl.by; out[3] = h->host_ctl.bz;
+  return GNDT_OK;
+}
+
 int64_t gndt_find_column(const gndt_column *cols, size_t n_cols, int32_t sx, int32_t sy) {
   return gndtl_find_column(cols, n_cols, sx, sy);
 }

@@ -280,6 +280,9 @@ int gndt_morton_string(int32_t sx, int32_t sy, char *buf);
 /* TwoDmap::countPositionXYZ (include/map2D.h:918-947): centre of cell (sx,sy,sz), metres. */
 int gndt_cell_center(const float origin[3], float grid_len, float z_len, int32_t sx, int32_t sy,
                      int32_t sz, float center[3]);
+/* Introspection: the sort-key layout the last build / update derived from the cloud's bounds:
+ * out[0] = live partition passes (of the 6 launched), out[1..3] = bits of the x, y, z fields. */
+int gndt_key_layout(gndt_handle *h, int out[4]);
 /* Integer-keyed replacements for the planner's string lookups `map_cell.find(morton_xy)` /
  * `map_slope.find(morton_z)` (include/map2D.h:269-272,396-398; include/GlobalPlan.h:58-61) and
  * for the neighbour keys of countLRFB (include/map2D.h:197-263), on the caller's copies of the
