@@ -158,9 +158,11 @@ class TwoDmap:
         self.uniformDivision(cloud)
         return self.create2DMap(demand)
 
-    def change2DMap(self, scan) -> bool:
+    def change2DMap(self, scan, stream: Optional[int] = None) -> bool:
         """Fuse one more scan into the resident map (map2D.h:672-822 / receiver.cpp:179-212)."""
         ptr, n, stride, mem, st, keep = self._marshal(scan)
+        if stream is not None:
+            st = stream
         _check(self._h, lib().gndt_update(self._h, ptr, n, stride, mem, st))
         self._keep = keep
         self._tables.clear()

@@ -99,28 +99,36 @@ class TiledTwoDmap:
         return self.map.plan_tiles(cloud, self.world)
 
     # ---- phase 1: everything that needs no size on the host ---------------------------------
-    def submit(self, cloud, demand="slope", origin=None, cuts=None, filter_points=True):
+    def submit(self, cloud, demand="slope", origin=None, cuts=None, filter_points=True, update=False):
         """Start a build on the next builder (asynchronous): local strip build (labels are per
         column: no communication), thin halo swapped with the two neighbour strips, own boundary
-        rows finished, strip sizes all-gathered on the device."""
+        rows finished, strip sizes all-gathered on the device.  update=True fuses `cloud` (one
+        more scan, the same on every rank: each keeps the points of its strip) into the strip
+        map that builder already holds instead of starting a new one (streaming, cfg 4)."""
         if len(self._inflight) == self.depth:
             raise RuntimeError("all builders busy: collect() before submitting another cloud")
+        if update and self.depth != 1:
+            raise RuntimeError("streaming updates need depth == 1: the resident map lives in one builder")
         s = self.slots[self._next]
         self._next = (self._next + 1) % self.depth
         m, L = s.map, lib()
-        if origin is not None:
-            m.setCloudFirst(origin)
-        if cuts is not None and filter_points:
-            m.setTile(int(cuts[self.rank]), int(cuts[self.rank + 1]))
-        else:
-            m.setTile(0, 0)
+        if not update:
+            if origin is not None:
+                m.setCloudFirst(origin)
+            if cuts is not None and filter_points:
+                m.setTile(int(cuts[self.rank]), int(cuts[self.rank + 1]))
+            else:
+                m.setTile(0, 0)
         stream = s.stream if s.stream is not None else torch.cuda.current_stream(s.device)
         if s.stream is not None:
             s.stream.wait_stream(torch.cuda.current_stream(s.device))  # the cloud was produced there
         with torch.cuda.stream(stream):
             st = stream.cuda_stream
-            m.uniformDivision(cloud)
-            m.create2DMap(demand, stream=st)
+            if update:
+                m.change2DMap(cloud, stream=st)
+            else:
+                m.uniformDivision(cloud)
+                m.create2DMap(demand, stream=st)
             slot_b = (self.halo_records + 1) * REC
             send_first, send_last, recv_prev, recv_next = (s.halo[i * slot_b:(i + 1) * slot_b] for i in range(4))
             _check(m._h, L.gndt_halo_pack(m._h, send_first.data_ptr(), send_last.data_ptr(), self.halo_records, st))
@@ -196,6 +204,13 @@ class TiledTwoDmap:
         (filter_points=True: points of other strips are dropped on the device) or only this
         strip's share."""
         self.submit(cloud, demand, origin=origin, cuts=cuts, filter_points=filter_points)
+        return self.collect()
+
+    def update(self, scan):
+        """Fuse one more scan into the strips and re-assemble the whole map on every rank
+        (change2DMap on N GPUs: every rank is handed the same scan and keeps its strip's
+        points; SURVEY.md §8(e), cfg 4).  Needs a map built with build(..., cuts=...)."""
+        self.submit(scan, update=True)
         return self.collect()
 
     def join(self):
