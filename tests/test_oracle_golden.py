@@ -147,3 +147,38 @@ def test_oracle_edge_cases():
     bad = np.array([[0, 0, 0, 1], [np.nan, 0, 0, 1], [np.inf, 1, 1, 1], [1e9, 0, 0, 1], [0.5, 0.5, 0.5, 1]], np.float32)
     m = O.oracle_build(bad, p)
     assert m.counts["n_dropped"] == 3 and m.counts["n_binned"] == 1
+
+
+@pytest.mark.skipif(not have_reference_lib(), reason="oracle/_ref not built")
+def test_port_equals_reference_on_small_degenerate_clouds():
+    """Fuzz: the restatement against the reference's own code on 150 tiny clouds that stress
+    what the synthetic scenes do not — 2..400 points, all four quadrants around the first point,
+    exact duplicates, points on cell edges, lines and planes (singular scatters, the
+    rough == 0 -> 0.01 rule), 1- and 2-point voxels next to fitted ones, both demands."""
+    rng = np.random.default_rng(20260000)
+    for case in range(150):
+        n = int(rng.integers(2, 400))
+        gl = float(rng.choice([0.1, 0.2, 0.5]))
+        zl = float(rng.choice([0.05, 0.1]))
+        kind = case % 5
+        pts = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+        if kind == 1:    # on a lattice of cell edges / exact duplicates
+            pts = (np.round(pts / gl) * gl).astype(np.float32)
+        elif kind == 2:  # a vertical line and a horizontal plane
+            pts[: n // 2, :2] = np.float32(0.3)
+            pts[n // 2:, 2] = np.float32(-0.2)
+        elif kind == 3:  # few voxels, many points each
+            pts *= np.float32(0.15)
+        elif kind == 4:  # far from the origin of coordinates
+            pts += np.array([431.7, -209.3, 12.1], np.float32)
+        cloud = np.concatenate([pts, np.ones((n, 1), np.float32)], axis=1)
+        cloud[0, :3] = pts.mean(axis=0)  # the map origin sits inside the cloud: four quadrants
+        p = default_params(gl, zl, 0.08, "true" if case % 2 else "slope")
+        a, b = O.oracle_build(cloud, p), O.ref_build(cloud, p)
+        assert a.counts == b.counts, case
+        for f in ("sx", "sy", "sz", "count", "mean", "scatter", "evals", "normal", "rough", "column", "slope"):
+            assert np.array_equal(a.voxels[f], b.voxels[f]), (case, f)
+        assert np.array_equal(a.voxels["flags"] & 0x1F3, b.voxels["flags"] & 0x1F3), case
+        sl = (a.voxels["flags"] & 2) != 0
+        assert np.array_equal((a.voxels["flags"] & 0x0C)[sl], (b.voxels["flags"] & 0x0C)[sl]), case
+        assert np.array_equal(a.morton_list, b.morton_list), case
