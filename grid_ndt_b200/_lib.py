@@ -57,14 +57,13 @@ SYMBOLS = {
     "gndt_copy_slopes": (_i, [_vp, _vp, _sz, _i, C.POINTER(_sz)]),
     "gndt_copy_columns": (_i, [_vp, _vp, _sz, _i, C.POINTER(_sz)]),
     "gndt_device_voxels": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
-    "gndt_label_edges": (_i, [_vp, _vp, _sz, _sz, _sz, _vp]),
-    "gndt_label_edges_strips": (_i, [_vp, _vp, C.POINTER(C.c_uint64), _i, _i, _vp]),
     "gndt_halo_pack": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "gndt_halo_edges": (_i, [_vp, _vp, _vp, _vp]),
     "gndt_apply_strip_offsets": (_i, [_vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _i, _vp]),
     "gndt_device_count_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "gndt_device_table_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "gndt_plan_tiles": (_i, [_vp, _vp, _sz, _sz, _i, _i, C.POINTER(C.c_int32), _vp]),
+    "gndt_set_stage_timing": (_i, [_vp, _i]),
     "gndt_stage_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "gndt_launch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "gndt_fast_div_status": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),

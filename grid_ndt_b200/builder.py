@@ -218,9 +218,6 @@ class TwoDmap:
         _check(self._h, lib().gndt_device_voxels(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def label_edges(self, table_ptr: int, n_table: int, begin: int, count: int, stream: int = 0):
-        _check(self._h, lib().gndt_label_edges(self._h, table_ptr, n_table, begin, count, stream))
-
     def plan_tiles(self, cloud, ntiles: int) -> np.ndarray:
         ptr, n, stride, mem, st, keep = self._marshal(cloud)
         cuts = (C.c_int32 * (ntiles + 1))()
@@ -228,6 +225,12 @@ class TwoDmap:
         _check(self._h, L.gndt_set_params(self._h, C.byref(self._p)))
         _check(self._h, L.gndt_plan_tiles(self._h, ptr, n, stride, mem, ntiles, cuts, st))
         return np.array(cuts[:], np.int32)
+
+    def stage_timing(self, on: bool = True):
+        """Record per-stage CUDA events in the following builds (off by default: the events keep
+        consecutive kernels from overlapping their launches)."""
+        _check(self._h, lib().gndt_set_stage_timing(self._h, 1 if on else 0))
+        return self
 
     def stage_ms(self) -> dict:
         ms = (C.c_float * _abi.N_STAGES)()

@@ -5,6 +5,7 @@
 // front end : bounds -> plan -> up to 6 partition passes -> reduce -> fixup   (cloud -> moments)
 // back end  : finalize+label -> column_finish -> edges                        (moments -> tables)
 // All stream-ordered with no host round trip; counts are read back only when asked for.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,17 +54,23 @@ struct gndt_handle {
   size_t cap_points = 0, cap_voxels = 0;
   // carved out of `zero`
   Ctl *ctl = nullptr;
-  u32 *hist = nullptr;
+  u32 *hist = nullptr;    // digit histograms [kMaxPasses][kMaxBins]
+  u32 *zhist = nullptr;   // exact z histogram of the bounds pass [kZHistBins]
   u32 *row_start = nullptr, *row_end = nullptr;
-  u32 *lb = nullptr;
-  u64 *glb = nullptr;   // look-back group words [kMaxPasses][sort_groups][256]
-  u32 *tile_state = nullptr;
+  // look-back words of the partition passes: two regions used alternately (pass p uses region
+  // p & 1); never memset from the host: the bounds pass zeroes region 0 for pass 0 and every
+  // pass zeroes the other region for its successor (sizes depend on the digit widths)
+  u32 *lb[2] = {nullptr, nullptr};
+  u64 *glb[2] = {nullptr, nullptr};
+  Buffer lookback;
+  u64 *tile_state = nullptr;         // reduce: look-back words per tile / per group of tiles
+  GroupState *tile_groups = nullptr;
   TileCarry *carry = nullptr;
-  u64 *blk_state = nullptr;
+  u64 *blk_state = nullptr;          // finalize: the same per block of voxels
+  GroupState *blk_groups = nullptr;
   size_t zero_bytes_used = 0;
   size_t sort_tiles = 0, sort_groups = 0, red_tiles = 0, label_blocks = 0;
-  // foreign-table scratch (gndt_label_edges)
-  Buffer f_slopes, f_columns, f_zero;
+  Buffer f_zero;  // scratch of gndt_plan_tiles (x-column histogram)
   // state
   bool built = false;
   bool counts_valid = false;
@@ -72,9 +79,12 @@ struct gndt_handle {
   cudaStream_t last_stream = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
   bool timed_h2d = false;
+  bool stage_timing = false;  // per-stage events (they sit between kernels and defeat the programmatic overlap there)
+  bool stages_valid = false;  // the last build / update recorded them
   uint64_t launches = 0;
   uint64_t total_points = 0;  // points handed to build + updates so far (host copy)
   int sm_count = 148;
+  int sort_ctas_per_sm[2] = {1, 1};  // resident CTAs of the partition pass kernels: [0] first pass, [1] later passes
   DivCheck div[2];            // [0] grid_len, [1] z_len
   uint64_t divcheck_values = 0;
 };
@@ -113,6 +123,26 @@ int ensure_keep(gndt_handle *h, Buffer &b, size_t bytes, size_t keep, cudaStream
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Launch with programmatic stream serialization (PDL): the kernel's CTAs may be scheduled while
+// its predecessor in the stream drains; every such kernel starts with pdl_wait(), so no memory
+// is touched before the predecessor has completed.  GNDT_NO_PDL=1 falls back to plain launches.
+bool use_pdl() {
+  static const bool on = [] { const char *e = getenv("GNDT_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+void launch(gndt_handle *h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface at the cudaGetLastError of the caller
+  h->launches += 1;
+}
 
 // Largest non-negative float a with (int)ceil(a / len) <= GNDT_MAX_INDEX, by bisection over
 // the bit patterns (the test is monotone in a).  Same IEEE binary32 operations as the device
@@ -234,25 +264,35 @@ int reserve(gndt_handle *h, size_t n, size_t cap_vox, bool host_input, size_t st
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_ctl = carve(sizeof(Ctl));
-  const size_t o_hist = carve((kMaxPasses + 1) * kRadixBins * sizeof(u32));
+  const size_t o_hist = carve((size_t)kMaxPasses * kMaxBins * sizeof(u32));
+  const size_t o_zh = carve(kZHistBins * sizeof(u32));
   const size_t o_rs = carve(65536 * sizeof(u32));
   const size_t o_re = carve(65536 * sizeof(u32));
-  const size_t o_lb = carve((size_t)kMaxPasses * h->sort_tiles * kRadixBins * sizeof(u32));
-  const size_t o_glb = carve((size_t)kMaxPasses * h->sort_groups * kRadixBins * sizeof(u64));
-  const size_t o_ts = carve(h->red_tiles * sizeof(u32));
+  const size_t o_ts = carve(h->red_tiles * sizeof(u64));
+  const size_t o_tg = carve((h->red_tiles / kScanGroup + 1) * sizeof(GroupState));
   const size_t o_ca = carve(h->red_tiles * sizeof(TileCarry));
   const size_t o_bs = carve(h->label_blocks * sizeof(u64));
+  const size_t o_bg = carve((h->label_blocks / kScanGroup + 1) * sizeof(GroupState));
   if ((rc = ensure(h, h->zero, off)) != GNDT_OK) return rc;
   char *z = static_cast<char *>(h->zero.p);
   h->ctl = reinterpret_cast<Ctl *>(z + o_ctl);
   h->hist = reinterpret_cast<u32 *>(z + o_hist);
+  h->zhist = reinterpret_cast<u32 *>(z + o_zh);
   h->row_start = reinterpret_cast<u32 *>(z + o_rs);
   h->row_end = reinterpret_cast<u32 *>(z + o_re);
-  h->lb = reinterpret_cast<u32 *>(z + o_lb);
-  h->glb = reinterpret_cast<u64 *>(z + o_glb);
-  h->tile_state = reinterpret_cast<u32 *>(z + o_ts);
+  {  // look-back regions (not part of the memset region)
+    const size_t lb_bytes = align_up(h->sort_tiles * kMaxBins * sizeof(u32) + 256, 256);
+    const size_t glb_bytes = align_up(h->sort_groups * kMaxBins * sizeof(u64) + 256, 256);
+    if ((rc = ensure(h, h->lookback, 2 * (lb_bytes + glb_bytes))) != GNDT_OK) return rc;
+    char *b = static_cast<char *>(h->lookback.p);
+    h->lb[0] = reinterpret_cast<u32 *>(b); h->lb[1] = reinterpret_cast<u32 *>(b + lb_bytes);
+    h->glb[0] = reinterpret_cast<u64 *>(b + 2 * lb_bytes); h->glb[1] = reinterpret_cast<u64 *>(b + 2 * lb_bytes + glb_bytes);
+  }
+  h->tile_state = reinterpret_cast<u64 *>(z + o_ts);
+  h->tile_groups = reinterpret_cast<GroupState *>(z + o_tg);
   h->carry = reinterpret_cast<TileCarry *>(z + o_ca);
   h->blk_state = reinterpret_cast<u64 *>(z + o_bs);
+  h->blk_groups = reinterpret_cast<GroupState *>(z + o_bg);
   h->zero_bytes_used = off;
   return GNDT_OK;
 }
@@ -283,38 +323,43 @@ int sync_counts(gndt_handle *h) {
 int front_end(gndt_handle *h, cudaStream_t st, const float *d_in, size_t n, size_t stride_f, size_t start,
               const DevParams &dp, VoxMoments *out) {
   GNDT_CUDA(h, cudaMemsetAsync(h->zero.p, 0, h->zero_bytes_used, st));
-  // K1: bounds + first-digit histogram, then the key layout
-  bounds_kernel<<<grid_for(h, n, 256 * 8, 8), 256, 0, st>>>(h->ctl, h->hist, d_in, stride_f, n, start, dp);
-  plan_kernel<<<1, 32, 0, st>>>(h->ctl);
-  h->launches += 2;
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_KEY], st));
-  // K2: partition passes (pass p writes buffer A when p is even, B when odd)
-  const int tiles = (int)((n + kSortTile - 1) / kSortTile);
+  // K1: bounds + exact z histogram (+ zeroes the first pass's look-back words), then the key layout
+  const size_t tiles = (n + kSortTile - 1) / kSortTile, groups = (tiles + kSortGroup - 1) / kSortGroup;
+  auto *bounds = dp.fast_div ? bounds_kernel<true> : bounds_kernel<false>;
+  launch(h, bounds, grid_for(h, n, 256 * 4, 8), 256, 0, st, h->ctl, h->zhist, d_in, stride_f, n, start, (void *)h->lb[0],
+         tiles * kFirstMaxBins * sizeof(u32), (void *)h->glb[0], groups * kFirstMaxBins * sizeof(u64), dp);
+  launch(h, plan_kernel, 1, kZHistBins, 0, st, h->ctl, (const u32 *)h->zhist, h->hist);
+  if (h->stage_timing) GNDT_CUDA(h, cudaEventRecord(h->ev[EV_KEY], st));
+  // K2: partition passes (pass p writes buffer A when p is even, B when odd).  Persistent CTAs:
+  // a pass beyond the planned count costs one launch of CTAs that return at once.
   float4 *A = static_cast<float4 *>(h->buf_a.p), *B = static_cast<float4 *>(h->buf_b.p);
   // the division mode is a template argument (two instantiations), not a run-time select
   auto *first_pass = dp.fast_div ? sort_pass_kernel<true, true> : sort_pass_kernel<true, false>;
   auto *next_pass = dp.fast_div ? sort_pass_kernel<false, true> : sort_pass_kernel<false, false>;
-  first_pass<<<tiles, kSortThreads, sizeof(SortSmem), st>>>(h->ctl, 0, d_in, stride_f, n, start, nullptr, A, h->lb, h->glb, h->hist, dp);
+  const int g0 = (int)std::min<size_t>(tiles, (size_t)h->sm_count * h->sort_ctas_per_sm[0]);
+  const int g1 = (int)std::min<size_t>(tiles, (size_t)h->sm_count * h->sort_ctas_per_sm[1]);
+  launch(h, first_pass, g0, kSortThreads, sizeof(SortSmem), st, h->ctl, 0, d_in, stride_f, n, start, (const float4 *)nullptr, A,
+         h->lb[0], h->glb[0], h->lb[1], h->glb[1], h->hist, dp);
   for (int p = 1; p < kMaxPasses; ++p) {
     const float4 *src = (p & 1) ? A : B;
     float4 *dst = (p & 1) ? B : A;
-    next_pass<<<tiles, kSortThreads, sizeof(SortSmem), st>>>(
-        h->ctl, p, nullptr, 4, n, 0, src, dst, h->lb + (size_t)p * h->sort_tiles * kRadixBins,
-        h->glb + (size_t)p * h->sort_groups * kRadixBins, h->hist, dp);
+    launch(h, next_pass, g1, kSortThreads, sizeof(SortSmem), st, h->ctl, p, (const float *)nullptr, (size_t)4, n, (size_t)0, src, dst,
+           h->lb[p & 1], h->glb[p & 1], h->lb[(p + 1) & 1], h->glb[(p + 1) & 1], h->hist, dp);
   }
-  h->launches += kMaxPasses;
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));
+  if (h->stage_timing) GNDT_CUDA(h, cudaEventRecord(h->ev[EV_SORT], st));
   // K3: per-voxel moments
   const int rtiles = (int)((n + kRedTile - 1) / kRedTile);
   auto *reduce = dp.fast_div ? reduce_kernel<true> : reduce_kernel<false>;
-  reduce<<<rtiles, kRedThreads, sizeof(RedSmem), st>>>(h->ctl, A, B, out, h->carry, h->tile_state, dp);
-  fixup_kernel<<<grid_for(h, (size_t)rtiles * 32, 128, 16), 128, 0, st>>>(h->ctl, out, h->carry);
-  h->launches += 2;
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_REDUCE], st));
+  launch(h, reduce, rtiles, kRedThreads, sizeof(RedSmem), st, h->ctl, (const float4 *)A, (const float4 *)B, out, h->carry,
+         h->tile_state, h->tile_groups, dp);
+  launch(h, fixup_kernel, grid_for(h, (size_t)rtiles * 32, 128, 16), 128, 0, st, h->ctl, out, (const TileCarry *)h->carry);
+  if (h->stage_timing) GNDT_CUDA(h, cudaEventRecord(h->ev[EV_REDUCE], st));
   return GNDT_OK;
 }
 
 __global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_fixed) {
+  pdl_wait();
+  pdl_trigger();
   const u32 n = n_fixed ? n_fixed : ctl->n_voxels;
   if (threadIdx.x == 0 && n && !ctl->err) {
     ctl->cx_min = contiguous_index(table[0].sx);
@@ -325,21 +370,15 @@ __global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_fix
 // sorted raw moments -> voxel / slope / column tables + reachability bits
 int back_end(gndt_handle *h, cudaStream_t st, const DevParams &dp, const VoxMoments *mom, bool bounds_from_table) {
   const int g_lab = grid_for(h, h->cap_voxels, kLabelThreads, 8);
-  finalize_label_kernel<<<g_lab, kLabelThreads, sizeof(FinSmem), st>>>(h->ctl, mom, (gndt_voxel *)h->table.p,
-                                                                       (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p,
-                                                                       (u32 *)h->vfirst.p, h->blk_state, &h->ctl->ticket[7], dp);
-  if (bounds_from_table) {
-    table_bounds_kernel<<<1, 32, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, 0u);
-    h->launches += 1;
-  }
-  column_finish_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const u32 *)h->vfirst.p, 0u,
-                                              (gndt_column *)h->columns.p, h->row_start, h->row_end, 0, 0);
-  h->launches += 2;
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_LABEL], st));
-  edges_kernel<<<g_lab, 256, 0, st>>>(h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
-                                      (const gndt_column *)h->columns.p, h->row_start, h->row_end, 0, 0, 0, 0u,
-                                      0xFFFFFFFFu, nullptr, 0, dp);
-  h->launches += 1;
+  launch(h, finalize_label_kernel, g_lab, kLabelThreads, sizeof(FinSmem), st, h->ctl, mom, (gndt_voxel *)h->table.p,
+         (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p, (u32 *)h->vfirst.p, h->blk_state, h->blk_groups,
+         &h->ctl->ticket[7], dp);
+  if (bounds_from_table) launch(h, table_bounds_kernel, 1, 32, 0, st, h->ctl, (const gndt_voxel *)h->table.p, 0u);
+  launch(h, column_finish_kernel, g_lab, 256, 0, st, h->ctl, (const gndt_voxel *)h->table.p, (const u32 *)h->vfirst.p, 0u,
+         (gndt_column *)h->columns.p, h->row_start, h->row_end, 0, 0);
+  if (h->stage_timing) GNDT_CUDA(h, cudaEventRecord(h->ev[EV_LABEL], st));
+  launch(h, edges_kernel, g_lab, 256, 0, st, h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
+         (const gndt_column *)h->columns.p, (const u32 *)h->row_start, (const u32 *)h->row_end, 0, 0, 0, dp);
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_EDGES], st));
   return GNDT_OK;
 }
@@ -396,6 +435,15 @@ int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(finalize_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem));
   if (e != cudaSuccess) { g_create_error = std::string("kernel image for sm_100a not loadable on this device: ") + cudaGetErrorString(e); delete h; return GNDT_ERR_CUDA; }
+  // persistent partition passes: as many CTAs as stay resident
+  for (int k = 0; k < 2; ++k) {
+    int nb = 0;
+    e = k == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sort_pass_kernel<true, true>, kSortThreads, sizeof(SortSmem))
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sort_pass_kernel<false, true>, kSortThreads, sizeof(SortSmem));
+    if (e != cudaSuccess || nb < 1) { g_create_error = "partition pass kernel does not fit on this device"; delete h; return GNDT_ERR_CUDA; }
+    h->sort_ctas_per_sm[k] = nb;
+    if (const char *w = getenv("GNDT_SORT_WAVES")) h->sort_ctas_per_sm[k] = nb * std::max(1, atoi(w));  // tuning: > 1 = more, shorter-lived CTAs
+  }
   int rc = verify_fast_div(h, h->params.grid_len, h->div[0]);
   if (rc == GNDT_OK) rc = verify_fast_div(h, h->params.z_len, h->div[1]);
   if (rc != GNDT_OK) { g_create_error = h->err; delete h; return rc; }
@@ -407,8 +455,7 @@ int gndt_destroy(gndt_handle *h) {
   if (!h) return GNDT_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
-                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small,
-                    &h->f_slopes, &h->f_columns, &h->f_zero};
+                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small, &h->lookback, &h->f_zero};
   for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
   for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -451,12 +498,12 @@ int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, i
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
   rc = front_end(h, st, d_in, n, stride_bytes / 4, start, dp, (VoxMoments *)h->mom.p);
   if (rc != GNDT_OK) return rc;
-  totals_kernel<<<1, 32, 0, st>>>((Totals *)h->small.p, h->ctl, (u64)n, 1);
-  h->launches += 1;
+  launch(h, totals_kernel, 1, 32, 0, st, (Totals *)h->small.p, (const Ctl *)h->ctl, (u64)n, 1);
   rc = back_end(h, st, dp, (const VoxMoments *)h->mom.p, false);
   if (rc != GNDT_OK) return rc;
   GNDT_CUDA(h, cudaGetLastError());
   h->built = true;
+  h->stages_valid = h->stage_timing;
   h->total_points = n;
   h->last_stream = st;
   return GNDT_OK;
@@ -523,6 +570,7 @@ int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, 
   if (rc != GNDT_OK) return rc;
   GNDT_CUDA(h, cudaGetLastError());
   std::swap(h->mom, h->mom_alt);
+  h->stages_valid = h->stage_timing;
   h->total_points += n;
   h->last_stream = st;
   return GNDT_OK;
@@ -583,67 +631,6 @@ int gndt_device_voxels(gndt_handle *h, const gndt_voxel **dptr, size_t *n) {
   *dptr = static_cast<const gndt_voxel *>(h->table.p);
   *n = h->host_ctl.n_voxels;
   return GNDT_OK;
-}
-
-// x rows that sit on a strip boundary of an all-gathered table: first and last row of every strip
-__global__ void halo_rows_kernel(const gndt_voxel *table, const u64 *offsets, int n_strips, int *rows) {
-  const int r = threadIdx.x;
-  if (r >= n_strips) return;
-  const u64 lo = offsets[r], hi = offsets[r + 1];
-  const int none = 0x7fffffff;
-  rows[2 * r] = (hi > lo) ? contiguous_index(table[lo].sx) : none;
-  rows[2 * r + 1] = (hi > lo) ? contiguous_index(table[hi - 1].sx) : none;
-}
-
-static int label_edges_impl(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin, size_t count,
-                            const uint64_t *offsets, int n_strips, cudaStream_t st) {
-  if (!h || (!table && n_table) || begin + count > n_table || n_table > 0xFFFFFFFEull || n_strips > 64) return GNDT_ERR_INVALID_ARG;
-  if (n_table == 0) return GNDT_OK;
-  GNDT_CUDA(h, cudaSetDevice(h->device));
-  int rc;
-  if ((rc = ensure(h, h->f_slopes, n_table * sizeof(gndt_slope))) != GNDT_OK) return rc;
-  if ((rc = ensure(h, h->f_columns, n_table * sizeof(gndt_column))) != GNDT_OK) return rc;
-  const size_t blocks = (n_table + kLabelThreads - 1) / kLabelThreads;
-  const size_t o_rs = align_up(sizeof(Ctl), 256), o_re = o_rs + 65536 * 4, o_hr = o_re + 65536 * 4, o_of = o_hr + 1024,
-               o_bs = o_of + 1024;
-  const size_t zbytes = o_bs + blocks * sizeof(u64);
-  if ((rc = ensure(h, h->f_zero, zbytes)) != GNDT_OK) return rc;
-  GNDT_CUDA(h, cudaMemsetAsync(h->f_zero.p, 0, zbytes, st));
-  char *z = static_cast<char *>(h->f_zero.p);
-  Ctl *ctl = reinterpret_cast<Ctl *>(z);
-  u32 *rs = reinterpret_cast<u32 *>(z + o_rs), *re = reinterpret_cast<u32 *>(z + o_re);
-  int *halo_rows = reinterpret_cast<int *>(z + o_hr);
-  u64 *d_off = reinterpret_cast<u64 *>(z + o_of);
-  u64 *bs = reinterpret_cast<u64 *>(z + o_bs);
-  const DevParams dp = make_dev(h, h->params, n_table);
-  const int g = grid_for(h, n_table, kLabelThreads, 8);
-  int n_halo = 0;
-  if (offsets && n_strips > 1) {
-    GNDT_CUDA(h, cudaMemcpyAsync(d_off, offsets, (size_t)(n_strips + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
-    halo_rows_kernel<<<1, 64, 0, st>>>(table, d_off, n_strips, halo_rows);
-    n_halo = 2 * n_strips;
-    h->launches += 1;
-  }
-  table_bounds_kernel<<<1, 32, 0, st>>>(ctl, table, (u32)n_table);
-  label_kernel<<<g, kLabelThreads, 0, st>>>(ctl, table, (u32)n_table, (gndt_slope *)h->f_slopes.p,
-                                            (gndt_column *)h->f_columns.p, bs, &ctl->ticket[7], 0, dp);
-  column_finish_kernel<<<g, 256, 0, st>>>(ctl, table, nullptr, (u32)n_table, (gndt_column *)h->f_columns.p, rs, re, 0, 0);
-  edges_kernel<<<g, 256, 0, st>>>(ctl, table, (gndt_slope *)h->f_slopes.p, (const gndt_column *)h->f_columns.p, rs, re,
-                                  0, 0, 0, (u32)begin, (u32)(begin + count), halo_rows, n_halo, dp);
-  h->launches += 4;
-  GNDT_CUDA(h, cudaGetLastError());
-  return GNDT_OK;
-}
-
-int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin, size_t count, void *stream) {
-  return label_edges_impl(h, table, n_table, begin, count, nullptr, 0, static_cast<cudaStream_t>(stream));
-}
-
-int gndt_label_edges_strips(gndt_handle *h, gndt_voxel *table, const uint64_t *offsets, int n_strips, int my_strip,
-                            void *stream) {
-  if (!h || !offsets || n_strips < 1 || my_strip < 0 || my_strip >= n_strips) return GNDT_ERR_INVALID_ARG;
-  return label_edges_impl(h, table, (size_t)offsets[n_strips], (size_t)offsets[my_strip],
-                          (size_t)(offsets[my_strip + 1] - offsets[my_strip]), offsets, n_strips, static_cast<cudaStream_t>(stream));
 }
 
 int gndt_halo_pack(gndt_handle *h, gndt_voxel *first_row_out, gndt_voxel *last_row_out, size_t cap_records, void *stream) {
@@ -751,16 +738,24 @@ int gndt_plan_tiles(gndt_handle *h, const void *xyz, size_t n, size_t stride_byt
   return GNDT_OK;
 }
 
+int gndt_set_stage_timing(gndt_handle *h, int on) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  h->stage_timing = on != 0;
+  return GNDT_OK;
+}
+
 int gndt_stage_ms(gndt_handle *h, float ms[GNDT_N_STAGES]) {
   if (!h || !ms) return GNDT_ERR_INVALID_ARG;
   if (!h->built) return GNDT_ERR_STATE;
   GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
   for (int i = 0; i < GNDT_N_STAGES; ++i) ms[i] = 0.f;
-  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_KEY], h->ev[EV_START], h->ev[EV_KEY]));
-  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_SORT], h->ev[EV_KEY], h->ev[EV_SORT]));
-  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_REDUCE], h->ev[EV_SORT], h->ev[EV_REDUCE]));
-  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_LABEL], h->ev[EV_REDUCE], h->ev[EV_LABEL]));
-  GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_EDGES], h->ev[EV_LABEL], h->ev[EV_EDGES]));
+  if (h->stages_valid) {
+    GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_KEY], h->ev[EV_START], h->ev[EV_KEY]));
+    GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_SORT], h->ev[EV_KEY], h->ev[EV_SORT]));
+    GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_REDUCE], h->ev[EV_SORT], h->ev[EV_REDUCE]));
+    GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_LABEL], h->ev[EV_REDUCE], h->ev[EV_LABEL]));
+    GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_EDGES], h->ev[EV_LABEL], h->ev[EV_EDGES]));
+  }
   GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_TOTAL], h->ev[EV_START], h->ev[EV_EDGES]));
   if (h->timed_h2d) GNDT_CUDA(h, cudaEventElapsedTime(&ms[GNDT_STAGE_H2D], h->ev[EV_H2D0], h->ev[EV_START]));
   return GNDT_OK;
@@ -836,7 +831,7 @@ int gndt_key_layout(gndt_handle *h, int out[4]) {
   if (!h || !out) return GNDT_ERR_INVALID_ARG;
   int rc = sync_counts(h);
   if (rc != GNDT_OK) return rc;
-  out[0] = h->host_ctl.n_passes; out[1] = h->host_ctl.bx; out[2] = h->host_ctl.by; out[3] = h->host_ctl.bz;
+  out[0] = h->host_ctl.n_passes; out[1] = h->host_ctl.bcol; out[2] = (int)h->host_ctl.ny; out[3] = h->host_ctl.bz;
   return GNDT_OK;
 }
 

@@ -16,25 +16,8 @@ namespace gndt {
 
 constexpr int kLabelThreads = 256;
 
-struct VoxHeader {
-  int sx, sy, sz;
-  u32 count, first;
-  float mx, my, mz;
-};
-
-__device__ __forceinline__ VoxHeader load_header(const gndt_voxel *t, size_t v) {
-  const int4 a = *reinterpret_cast<const int4 *>(t + v);
-  const int4 b = *(reinterpret_cast<const int4 *>(t + v) + 1);
-  VoxHeader h;
-  h.sx = a.x; h.sy = a.y; h.sz = a.z; h.count = (u32)a.w;
-  h.first = (u32)b.x; h.mx = __int_as_float(b.y); h.my = __int_as_float(b.z); h.mz = __int_as_float(b.w);
-  return h;
-}
 __device__ __forceinline__ int contiguous_index(int s) { return s > 0 ? s - 1 : s; }
 
-// K4: one thread per voxel.  `relabel` = false only rebuilds the column/slope tables from
-// flags already present (used on all-gathered multi-GPU tables).
-//
 // isSlope restated in closed form: processing order inside a column is
 // ascending first_index; a neighbour u contributes its centroid z only if it was fitted
 // BEFORE v (count >= min_points and first(u) < first(v)), else the constructor's 0.
@@ -42,108 +25,8 @@ __device__ __forceinline__ int contiguous_index(int s) { return s > 0 ? s - 1 : 
 //   down(v) = same at cz-1;   is_slope = fitted && !up          (demand "slope")
 // demand "true": every fitted voxel is a Slope, down = false, up = countUp on FINAL
 // centroids (no order dependence).
-__global__ void __launch_bounds__(kLabelThreads)
-label_kernel(Ctl *ctl, gndt_voxel *table, u32 n_table_fixed, gndt_slope *slopes, gndt_column *columns,
-             u64 *blk_state, u32 *counters, int relabel, DevParams P) {
-  __shared__ u32 warp_sums[8];
-  __shared__ u32 s_tile;
-  __shared__ u64 s_prefix;
-  const int tid = threadIdx.x;
-  const u32 V = n_table_fixed ? n_table_fixed : ctl->n_voxels;
-  const u32 n_blocks = (V + kLabelThreads - 1) / kLabelThreads;
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_tile = atomicAdd(&counters[0], 1u);
-    __syncthreads();
-    const u32 blk = s_tile;
-    if (blk >= n_blocks) return;
-    const size_t v = (size_t)blk * kLabelThreads + tid;
-    const bool live = v < V;
-    VoxHeader h = {};
-    u32 flags = 0;
-    bool head = false;
-    if (live) {
-      h = load_header(table, v);
-      const u32 old_flags = table[v].flags;
-      VoxHeader lo = {}, hi = {};
-      bool has_lo = false, has_hi = false;
-      if (v > 0) { lo = load_header(table, v - 1); has_lo = (lo.sx == h.sx && lo.sy == h.sy); }
-      if (v + 1 < V) { hi = load_header(table, v + 1); has_hi = (hi.sx == h.sx && hi.sy == h.sy); }
-      head = !has_lo;
-      if (relabel) {
-        const bool fitted = (int)h.count >= P.min_points;
-        if (fitted) {
-          flags = GNDT_F_FITTED;
-          const int cz = contiguous_index(h.sz);
-          bool up = false, down = false;
-          const bool ordered = (P.demand == GNDT_DEMAND_SLOPE);
-          if (has_hi && contiguous_index(hi.sz) == cz + 1) {
-            const bool seen = (int)hi.count >= P.min_points && (!ordered || hi.first < h.first);
-            up = fabsf(__fsub_rn(seen ? hi.mz : 0.f, h.mz)) > P.slope_interval;
-          }
-          if (ordered && has_lo && contiguous_index(lo.sz) == cz - 1) {
-            const bool seen = (int)lo.count >= P.min_points && lo.first < h.first;
-            down = fabsf(__fsub_rn(seen ? lo.mz : 0.f, h.mz)) > P.slope_interval;
-          }
-          if (up) flags |= GNDT_F_UP;
-          if (down) flags |= GNDT_F_DOWN;
-          if (P.demand == GNDT_DEMAND_TRUE || !up) flags |= GNDT_F_SLOPE;
-        }
-      } else {
-        flags = old_flags & ~(u32)GNDT_F_COLUMN_HEAD;
-      }
-      if (head) flags |= GNDT_F_COLUMN_HEAD;
-    }
-    const bool slope = (flags & GNDT_F_SLOPE) != 0;
-    u32 total = 0;
-    const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
-    const u32 exc = block_exclusive_scan_256(packed, warp_sums, &total);
-    if (tid < 32) {  // warp 0 resolves the (columns, slopes) prefix of this block, 32 blocks per round trip
-      const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
-      const u64 pre = warp_lookback_u64(blk_state, (int)blk, mine, &ctl->err);
-      if (tid == 0) {
-        s_prefix = pre;
-        if (blk == n_blocks - 1) {
-          const u64 incl = pre + mine;
-          ctl->n_columns = (u32)(incl >> 31);
-          ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
-        }
-      }
-    }
-    const u32 fitted_cnt = __syncthreads_count(live && (flags & GNDT_F_FITTED));
-    if (tid == 0 && fitted_cnt) atomicAdd(&ctl->n_fitted, fitted_cnt);
-    if (!live) continue;
-    const u32 cols_before = (u32)(s_prefix >> 31) + (exc >> 16);
-    const u32 slopes_before = (u32)(s_prefix & 0x7FFFFFFFu) + (exc & 0xFFFFu);
-    const u32 col_idx = cols_before + (head ? 1u : 0u) - 1u;
-    gndt_voxel *rec = table + v;
-    rec->flags = flags;
-    rec->column = col_idx;
-    rec->slope = slope ? slopes_before : 0xFFFFFFFFu;
-    if (slope) {
-      gndt_slope s;
-      s.sx = h.sx; s.sy = h.sy; s.sz = h.sz;
-      s.mean[0] = h.mx; s.mean[1] = h.my; s.mean[2] = h.mz;
-      s.normal[0] = rec->normal[0]; s.normal[1] = rec->normal[1]; s.normal[2] = rec->normal[2];
-      s.rough = rec->rough;
-      s.flags = flags;
-      s.voxel = (u32)v;
-      float4 *d = reinterpret_cast<float4 *>(slopes + slopes_before);
-      const float4 *q = reinterpret_cast<const float4 *>(&s);
-      d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
-    }
-    if (head) {
-      gndt_column c;
-      c.sx = h.sx; c.sy = h.sy; c.first_index = h.first; c.voxel_begin = (u32)v; c.voxel_count = 0;
-      c.slope_begin = slopes_before; c.slope_count = 0; c.reserved = 0;
-      float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
-      const float4 *q = reinterpret_cast<const float4 *>(&c);
-      d[0] = q[0]; d[1] = q[1];
-    }
-  }
-}
-
-// K4 (main path): one thread per voxel, straight from the raw binary64 moments:
+//
+// K4: one thread per voxel, straight from the raw binary64 moments:
 //   * finish the voxel — binary32 mean / scatter, closed-form eigen, rough, normal
 //     (create2DMap's fit + countRoughNormal, map2D.h:621-623,110-133)
 //   * label it — the isSlope / countUp rules restated above, against the adjacent records
@@ -163,7 +46,9 @@ struct __align__(128) FinSmem {
 #endif
 __global__ void __launch_bounds__(kLabelThreads, GNDT_FIN_MINBLOCKS)
 finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_slope *slopes,
-                      gndt_column *columns, u32 *vfirst, u64 *blk_state, u32 *counters, DevParams P) {
+                      gndt_column *columns, u32 *vfirst, u64 *blk_state, GroupState *blk_groups, u32 *counters, DevParams P) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_fin[];
   FinSmem &S = *reinterpret_cast<FinSmem *>(smem_fin);
   const int tid = threadIdx.x;
@@ -228,8 +113,8 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
     u32 total = 0;
     const u32 exc = block_exclusive_scan_256(packed, S.warp_sums, &total);
     if (tid < 32) {  // warp 0 resolves the (columns, slopes) prefix of this block, 32 blocks per round trip
-      const u64 mine = ((u64)(total >> 16) << 31) | (u64)(total & 0xFFFFu);
-      const u64 pre = warp_lookback_u64(blk_state, (int)blk, mine, &ctl->err);
+      const u64 mine = pack_pair(total >> 16, total & 0xFFFFu);
+      const u64 pre = warp_lookback_grouped(blk_state, blk_groups, (int)blk, total >> 16, total & 0xFFFFu, &ctl->err);
       if (tid == 0) {
         S.prefix = pre;
         if (blk == n_blocks - 1) {
@@ -315,6 +200,8 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
 __global__ void column_finish_kernel(Ctl *ctl, const gndt_voxel *table, const u32 *vfirst, u32 n_table_fixed,
                                      gndt_column *columns, u32 *row_start, u32 *row_end, int cx_base_fixed,
                                      int use_fixed_base) {
+  pdl_wait();
+  pdl_trigger();
   const u32 V = n_table_fixed ? n_table_fixed : ctl->n_voxels;
   const u32 C = ctl->n_columns, S = ctl->n_slopes;
   const int cx_base = use_fixed_base ? cx_base_fixed : ctl->cx_min;
@@ -382,20 +269,15 @@ __device__ __forceinline__ bool cell_reachable(const gndt_column &c, const gndt_
 __global__ void __launch_bounds__(256)
 edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column *columns,
              const u32 *row_start, const u32 *row_end, int cx_base_fixed, int cx_max_fixed, int use_fixed,
-             u32 vox_begin, u32 vox_end, const int *halo_rows, int n_halo, DevParams P) {
+             DevParams P) {
+  pdl_wait();
+  pdl_trigger();
   const u32 S = ctl->n_slopes, C = ctl->n_columns;
   const int cx_base = use_fixed ? cx_base_fixed : ctl->cx_min;
   const int cx_max = use_fixed ? cx_max_fixed : ctl->cx_max;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
     gndt_slope me = slopes[i];
     const int cx = contiguous_index(me.sx), cy = contiguous_index(me.sy);
-    if (me.voxel < vox_begin || me.voxel >= vox_end) {
-      // outside the caller's range: still refreshed when it lies on a strip-boundary x row
-      // (multi-GPU halo: those rows were labelled by their owner without their neighbour strip)
-      bool halo = false;
-      for (int k = 0; k < n_halo; ++k) halo |= (halo_rows[k] == cx);
-      if (!halo) continue;
-    }
     const u32 ci = table[me.voxel].column;
     const float n[3] = {me.normal[0], me.normal[1], me.normal[2]};
     const double n_len = normal_length(n);

@@ -174,7 +174,7 @@ struct RedSmem {
 template <bool FAST>
 __device__ __forceinline__ u64 point_key(const float4 &p, const float o[3], const DevParams &P) {
   int cx, cy, cz;
-  point_indices_t<FAST>(p.x, p.y, p.z, o, P, cx, cy, cz);
+  point_indices_masked_t<FAST>(p.x, p.y, p.z, o, P, 7, cx, cy, cz);  // partitioned points are all valid
   return voxel_key(cx, cy, cz);
 }
 
@@ -222,7 +222,9 @@ __device__ __forceinline__ u32 warp_lookback_u32(u32 *state, int tile, u32 my_co
 template <bool FAST>
 __global__ void __launch_bounds__(kRedThreads, GNDT_RED_MINBLOCKS)
 reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mom, TileCarry *carry,
-              u32 *tile_state, DevParams P) {
+              u64 *tile_state, GroupState *tile_groups, DevParams P) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RedSmem &S = *reinterpret_cast<RedSmem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -298,10 +300,7 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
   const bool first_is_head = S.prev_key != S.first_key;
   const bool last_complete = S.next_key != S.last_key;
   const u32 heads = (u32)n_runs - (first_is_head ? 0u : 1u);
-  if (tid == 0) {
-    S.run_start[n_runs] = (unsigned short)cnt;
-    st_relaxed(tile_state + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | heads);  // publish early, resolve later
-  }
+  if (tid == 0) S.run_start[n_runs] = (unsigned short)cnt;
   __syncthreads();
 
   // ---- one thread per run: shifted one-pass sums from shared memory (first round kept in
@@ -326,11 +325,9 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
   Moments mo0;
   const bool have0 = (tid < n_runs) && run_moments(tid, mo0);
 
-  if (warp == 0 && tile > 0) {
-    const u32 vb = warp_lookback_u32(tile_state, tile, heads, &ctl->err);
-    if (lane == 0) S.vox_base = vb;
-  } else if (tid == 0) {
-    S.vox_base = 0;
+  if (warp == kRedThreads / 32 - 1) {  // the last warp has the fewest runs of its own: it resolves the voxel base
+    const u64 vb = warp_lookback_grouped(tile_state, tile_groups, tile, 0u, heads, &ctl->err);
+    if (lane == 0) S.vox_base = (u32)vb;
   }
   __syncthreads();
   const u32 vox_base = S.vox_base;
@@ -390,6 +387,8 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
 // a time (one per lane, loaded in parallel), merges them with a fixed shuffle tree
 // (deterministic) and folds them into the voxel's stored moments.
 __global__ void __launch_bounds__(128) fixup_kernel(Ctl *ctl, VoxMoments *mom, const TileCarry *carry) {
+  pdl_wait();
+  pdl_trigger();
   const size_t M = (size_t)ctl->n_valid;
   const int n_tiles = (int)((M + kRedTile - 1) / kRedTile);
   const int lane = threadIdx.x & 31;

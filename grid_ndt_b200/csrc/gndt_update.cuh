@@ -21,6 +21,8 @@ struct Totals {
 };
 
 __global__ void totals_kernel(Totals *tot, const Ctl *ctl, u64 n_points, int reset) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x || blockIdx.x) return;
   if (reset) { tot->n_points = 0; tot->n_valid = 0; tot->n_dropped = 0; tot->n_outside = 0; }
   tot->n_points += n_points; tot->n_valid += ctl->n_valid; tot->n_dropped += ctl->n_dropped; tot->n_outside += ctl->n_outside;

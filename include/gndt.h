@@ -208,21 +208,6 @@ int gndt_copy_columns(gndt_handle *h, gndt_column *dst, size_t cap, int dst_mem,
 int gndt_device_voxels(gndt_handle *h, const gndt_voxel **dptr, size_t *n);
 
 /*
- * Recompute the neighbour reachability bits (GNDT_F_REACH_*) of records
- * [begin, begin+count) of an arbitrary device voxel table `table` of `n_table` records
- * sorted like ours (e.g. the all-gathered tiles of several GPUs, so that strip
- * boundaries see their halo).  Replaces countLRFB + countReachable + countAngle
- * (include/map2D.h:197-296,477-482).
- */
-int gndt_label_edges(gndt_handle *h, gndt_voxel *table, size_t n_table, size_t begin,
-                     size_t count, void *stream);
-/* Same, for a table assembled from `n_strips` all-gathered x strips (strip r = records
- * [offsets[r], offsets[r+1]), offsets on the host): refreshes strip `my_strip` AND every
- * record on a strip-boundary x row (first/last row of each strip), so that after the call
- * this GPU's copy of the whole map is consistent without any further exchange. */
-int gndt_label_edges_strips(gndt_handle *h, gndt_voxel *table, const uint64_t *offsets, int n_strips,
-                            int my_strip, void *stream);
-/*
  * Thin-halo protocol for x strips (no host synchronisation, all stream-ordered):
  *   gndt_halo_pack  writes this strip's first and last x row into two caller buffers of
  *                   (1 + cap_records) gndt_voxel slots each (slot 0 is a header);
@@ -253,6 +238,11 @@ int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capac
 int gndt_plan_tiles(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem,
                     int ntiles, int32_t *cuts, void *stream);
 
+/* Stage events sit between the kernels of a build and keep each stage from overlapping the
+ * launch of the next, so they are recorded only on request (default off): with on == 0
+ * gndt_stage_ms reports GNDT_STAGE_TOTAL (+ H2D) and zeros for the individual stages.
+ * Replaces: the stopwatch() pairs around "division" / "calculate" (src/receiver.cpp:148-162). */
+int gndt_set_stage_timing(gndt_handle *h, int on);
 int gndt_stage_ms(gndt_handle *h, float ms[GNDT_N_STAGES]);
 /* number of kernel launches issued by the last build/update on this handle */
 int gndt_launch_count(gndt_handle *h, uint64_t *n_launches);
