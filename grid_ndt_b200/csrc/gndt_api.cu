@@ -370,7 +370,7 @@ __global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_fix
 // sorted raw moments -> voxel / slope / column tables + reachability bits
 int back_end(gndt_handle *h, cudaStream_t st, const DevParams &dp, const VoxMoments *mom, bool bounds_from_table) {
   const int g_lab = grid_for(h, h->cap_voxels, kLabelThreads, 8);
-  launch(h, finalize_label_kernel, g_lab, kLabelThreads, sizeof(FinSmem), st, h->ctl, mom, (gndt_voxel *)h->table.p,
+  launch(h, finalize_label_kernel, g_lab, kFinThreads, sizeof(FinSmem), st, h->ctl, mom, (gndt_voxel *)h->table.p,
          (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p, (u32 *)h->vfirst.p, h->blk_state, h->blk_groups,
          &h->ctl->ticket[7], dp);
   if (bounds_from_table) launch(h, table_bounds_kernel, 1, 32, 0, st, h->ctl, (const gndt_voxel *)h->table.p, 0u);

@@ -37,14 +37,17 @@ struct __align__(128) FinSmem {
   float4 out[kLabelThreads * 6];     // the block's 256 finished 96-byte records
   unsigned long long mbar;
   u64 prefix;
-  u32 warp_sums[8];
-  u32 tile;
+  u32 warp_sums[32];
+  u32 tile, total;
 };
 
 #ifndef GNDT_FIN_MINBLOCKS
-#define GNDT_FIN_MINBLOCKS 4
+#define GNDT_FIN_MINBLOCKS 3
 #endif
-__global__ void __launch_bounds__(kLabelThreads, GNDT_FIN_MINBLOCKS)
+// 256 voxel threads + one helper warp: the helper publishes the block's (columns, slopes)
+// counts and resolves their prefix (two L2 round trips) WHILE the voxel warps do the eigen work.
+constexpr int kFinThreads = kLabelThreads + 32;
+__global__ void __launch_bounds__(kFinThreads, GNDT_FIN_MINBLOCKS)
 finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_slope *slopes,
                       gndt_column *columns, u32 *vfirst, u64 *blk_state, GroupState *blk_groups, u32 *counters, DevParams P) {
   pdl_wait();
@@ -52,6 +55,7 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
   extern __shared__ __align__(128) unsigned char smem_fin[];
   FinSmem &S = *reinterpret_cast<FinSmem *>(smem_fin);
   const int tid = threadIdx.x;
+  const bool helper = tid >= kLabelThreads;
   if (ctl->err) return;  // e.g. capacity exceeded: the moments table is incomplete
   const u32 V = ctl->n_voxels;
   const u32 n_blocks = (V + kLabelThreads - 1) / kLabelThreads;
@@ -71,11 +75,9 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
     }
     if (!mbar_wait(&S.mbar, it & 1)) atomicOr(&ctl->err, kErrWatchdog);
     const u32 v = v0 + tid;
-    const bool live = tid < (int)cnt;
+    const bool live = !helper && tid < (int)cnt;
 
-    // ---- phase 1 (cheap): labels from the record headers, then the block's (columns,
-    // slopes) prefix.  Resolving the prefix BEFORE the expensive eigen work keeps the window
-    // in which successors see only an aggregate short, hence their look-back walks short.
+    // ---- phase 1 (cheap): labels from the record headers
     u64 key = 0;
     u32 count = 0, first = 0, flags = 0;
     float mz = 0.f;
@@ -110,28 +112,24 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
     }
     const bool slope = (flags & GNDT_F_SLOPE) != 0;
     const u32 packed = ((head ? 1u : 0u) << 16) | (slope ? 1u : 0u);
-    u32 total = 0;
-    const u32 exc = block_exclusive_scan_256(packed, S.warp_sums, &total);
-    if (tid < 32) {  // warp 0 resolves the (columns, slopes) prefix of this block, 32 blocks per round trip
-      const u64 mine = pack_pair(total >> 16, total & 0xFFFFu);
+    const u32 exc = block_exclusive_scan(packed, S.warp_sums);
+    if (tid == kLabelThreads - 1) S.total = exc + packed;
+    __syncthreads();
+
+    if (helper) {
+      // ---- the block's (columns, slopes) prefix, resolved behind the voxel warps' eigen work
+      const u32 total = S.total;
       const u64 pre = warp_lookback_grouped(blk_state, blk_groups, (int)blk, total >> 16, total & 0xFFFFu, &ctl->err);
-      if (tid == 0) {
+      if (tid == kLabelThreads) {
         S.prefix = pre;
         if (blk == n_blocks - 1) {
-          const u64 incl = pre + mine;
+          const u64 incl = pre + pack_pair(total >> 16, total & 0xFFFFu);
           ctl->n_columns = (u32)(incl >> 31);
           ctl->n_slopes = (u32)(incl & 0x7FFFFFFFu);
         }
       }
-    }
-    const u32 fitted_cnt = __syncthreads_count(live && fitted);
-    if (tid == 0 && fitted_cnt) atomicAdd(&ctl->n_fitted, fitted_cnt);
-
-    // ---- phase 2: finish the voxel (binary32 mean / scatter, eigen) into shared memory
-    if (live) {
-      const u32 cols_before = (u32)(S.prefix >> 31) + (exc >> 16);
-      const u32 slopes_before = (u32)(S.prefix & 0x7FFFFFFFu) + (exc & 0xFFFFu);
-      const u32 col_idx = cols_before + (head ? 1u : 0u) - 1u;
+    } else if (live) {
+      // ---- phase 2: finish the voxel (binary32 mean / scatter, eigen) into shared memory
       float f[24];
 #pragma unroll
       for (int i = 0; i < 24; ++i) f[i] = 0.f;
@@ -169,20 +167,38 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
         f[19] = (float)(k == 0 ? Vv[2][0] : (k == 1 ? Vv[2][1] : Vv[2][2]));
         f[20] = rough;
       }
-      u[21] = flags; u[22] = col_idx; u[23] = slope ? slopes_before : 0xFFFFFFFFu;
+      u[21] = flags;
 #pragma unroll
       for (int i = 0; i < 6; ++i) S.out[tid * 6 + i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
       vfirst[v] = first;
-      if (slope) {
-        float4 *d = reinterpret_cast<float4 *>(slopes + slopes_before);
-        d[0] = make_float4(f[0], f[1], f[2], f[5]);          // sx sy sz mean.x
-        d[1] = make_float4(f[6], f[7], f[17], f[18]);        // mean.y mean.z normal.x normal.y
-        d[2] = make_float4(f[19], f[20], __uint_as_float(flags), __uint_as_float(v));
-      }
-      if (head) {
-        float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
-        d[0] = make_float4(f[0], f[1], f[4], __uint_as_float(v));                   // sx sy first voxel_begin
-        d[1] = make_float4(0.f, __uint_as_float(slopes_before), 0.f, 0.f);          // count slope_begin count rsvd
+    }
+    const u32 fitted_cnt = __syncthreads_count(live && fitted);  // joins the helper: S.prefix is final
+    if (tid == 0 && fitted_cnt) atomicAdd(&ctl->n_fitted, fitted_cnt);
+
+    // ---- phase 3: the compacted indices, Slope and Cell records
+    if (live) {
+      const u32 cols_before = (u32)(S.prefix >> 31) + (exc >> 16);
+      const u32 slopes_before = (u32)(S.prefix & 0x7FFFFFFFu) + (exc & 0xFFFFu);
+      const u32 col_idx = cols_before + (head ? 1u : 0u) - 1u;
+      float4 *rec = S.out + tid * 6;
+      float4 last = rec[5];  // rough flags column slope
+      last.z = __uint_as_float(col_idx);
+      last.w = __uint_as_float(slope ? slopes_before : 0xFFFFFFFFu);
+      rec[5] = last;
+      if (slope || head) {
+        const float4 r0 = rec[0], r1 = rec[1];  // sx sy sz count | first mean.xyz
+        if (slope) {
+          const float4 r4 = rec[4];             // evals[2] normal.xyz
+          float4 *d = reinterpret_cast<float4 *>(slopes + slopes_before);
+          d[0] = make_float4(r0.x, r0.y, r0.z, r1.y);        // sx sy sz mean.x
+          d[1] = make_float4(r1.z, r1.w, r4.y, r4.z);        // mean.y mean.z normal.x normal.y
+          d[2] = make_float4(r4.w, last.x, __uint_as_float(flags), __uint_as_float(v));
+        }
+        if (head) {
+          float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
+          d[0] = make_float4(r0.x, r0.y, r1.x, __uint_as_float(v));                   // sx sy first voxel_begin
+          d[1] = make_float4(0.f, __uint_as_float(slopes_before), 0.f, 0.f);          // count slope_begin count rsvd
+        }
       }
     }
     // ---- the 256 records leave shared memory as one TMA bulk store

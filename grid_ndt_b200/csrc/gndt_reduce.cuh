@@ -18,7 +18,7 @@
 namespace gndt {
 
 #ifndef GNDT_RED_MINBLOCKS
-#define GNDT_RED_MINBLOCKS 4
+#define GNDT_RED_MINBLOCKS 5
 #endif
 #ifndef GNDT_RED_LONGRUN
 #define GNDT_RED_LONGRUN 64
@@ -160,8 +160,9 @@ __device__ void eig3_sym(const double a[6], double w[3], double V[3][3]) {
   }
 }
 
-struct RedSmem {
-  float4 pts[kRedTile];
+struct __align__(128) RedSmem {
+  float4 pts_raw[kRedTile + 2];  // [0] last point of the previous tile, [1..cnt] the tile, [cnt+1] first point of the next
+  unsigned long long mbar;
   unsigned short run_start[kRedTile + 2];
   unsigned short long_list[kMaxLong];
   u64 row_last_key[kRedItems][8];  // key of the last lane of every (row, warp) for head detection
@@ -228,7 +229,7 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RedSmem &S = *reinterpret_cast<RedSmem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { S.tile_id = atomicAdd(&ctl->ticket[6], 1u); S.n_long = 0; }
+  if (tid == 0) { S.tile_id = atomicAdd(&ctl->ticket[6], 1u); S.n_long = 0; mbar_init(&S.mbar, 1); }
   __syncthreads();
   const int tile = (int)S.tile_id;
   const size_t M = (size_t)ctl->n_valid;
@@ -237,32 +238,27 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
   const int cnt = (int)min((size_t)kRedTile, M - base);
   const float4 *src = ((ctl->n_passes - 1) & 1) ? buf_b : buf_a;  // pass p writes A when p is even
   const float o[3] = {ctl->origin[0], ctl->origin[1], ctl->origin[2]};
+  float4 *pts = S.pts_raw + 1;
 
-  // ---- stage the tile (all loads first), voxel key per point in registers
-  float4 pt[kRedItems];
-#pragma unroll
-  for (int k = 0; k < kRedItems; ++k) {
-    const int i = k * kRedThreads + tid;
-    if (i < cnt) pt[k] = ld_stream(src + base + i);
-  }
-  float4 edge = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tid == 0 && base > 0) edge = src[base - 1];
-  if (tid == 32 && base + cnt < M) edge = src[base + cnt];
+  // ---- stage the tile and its two neighbour points with one TMA bulk copy
+  const bool has_prev = base > 0, has_next = base + cnt < M;
+  if (tid == 0)
+    tma_load_1d(S.pts_raw + (has_prev ? 0 : 1), src + base - (has_prev ? 1 : 0),
+                (u32)(cnt + (has_prev ? 1 : 0) + (has_next ? 1 : 0)) * 16u, &S.mbar);
+  if (!mbar_wait(&S.mbar, 0)) atomicOr(&ctl->err, kErrWatchdog);
+  // voxel key per point in registers
   u64 key[kRedItems];
 #pragma unroll
   for (int k = 0; k < kRedItems; ++k) {
     const int i = k * kRedThreads + tid;
     key[k] = ~0ull;
-    if (i < cnt) {
-      S.pts[i] = pt[k];
-      key[k] = point_key<FAST>(pt[k], o, P);
-    }
+    if (i < cnt) key[k] = point_key<FAST>(pts[i], o, P);
     if (lane == 31) S.row_last_key[k][warp] = key[k];
     if (i == 0) S.first_key = key[k];
     if (i == cnt - 1) S.last_key = key[k];
   }
-  if (tid == 0) S.prev_key = (base > 0) ? point_key<FAST>(edge, o, P) : ~0ull;
-  if (tid == 32) S.next_key = (base + cnt < M) ? point_key<FAST>(edge, o, P) : ~0ull;
+  if (tid == 0) S.prev_key = has_prev ? point_key<FAST>(S.pts_raw[0], o, P) : ~0ull;
+  if (tid == 32) S.next_key = has_next ? point_key<FAST>(pts[cnt], o, P) : ~0ull;
   __syncthreads();
 
   // ---- run heads (position 0 always starts a run of this tile)
@@ -311,10 +307,10 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
       S.long_list[atomicAdd(&S.n_long, 1u)] = (unsigned short)j;
       return false;
     }
-    const float4 p0 = S.pts[s];
+    const float4 p0 = pts[s];
     double sd[3] = {0, 0, 0}, sq[6] = {0, 0, 0, 0, 0, 0};
     for (int i = s + 1; i < e; ++i) {
-      const float4 p = S.pts[i];
+      const float4 p = pts[i];
       const double dx = (double)p.x - (double)p0.x, dy = (double)p.y - (double)p0.y, dz = (double)p.z - (double)p0.z;
       sd[0] += dx; sd[1] += dy; sd[2] += dz;
       sq[0] += dx * dx; sq[1] += dx * dy; sq[2] += dx * dz; sq[3] += dy * dy; sq[4] += dy * dz; sq[5] += dz * dz;
@@ -345,7 +341,7 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
       return;
     }
     if (slot >= P.max_voxels) { atomicOr(&ctl->err, kErrCapacity); return; }
-    store_moments(mom + slot, point_key<FAST>(S.pts[s], o, P), __float_as_uint(S.pts[s].w), mo);
+    store_moments(mom + slot, point_key<FAST>(pts[s], o, P), __float_as_uint(pts[s].w), mo);
     if (open_end) {
       my_carry->tail_slot = slot;
       atomicOr(&my_carry->flags, kCarryHasTail);
@@ -364,10 +360,10 @@ reduce_kernel(Ctl *ctl, const float4 *buf_a, const float4 *buf_b, VoxMoments *mo
   for (int l = warp; l < n_long; l += kRedThreads / 32) {
     const int j = S.long_list[l];
     const int s = S.run_start[j], e = S.run_start[j + 1];
-    const float4 p0 = S.pts[s];
+    const float4 p0 = pts[s];
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = s + lane; i < e; i += 32) {
-      const float4 p = S.pts[i];
+      const float4 p = pts[i];
       const double dx = (double)p.x - (double)p0.x, dy = (double)p.y - (double)p0.y, dz = (double)p.z - (double)p0.z;
       acc[0] += dx; acc[1] += dy; acc[2] += dz;
       acc[3] += dx * dx; acc[4] += dx * dy; acc[5] += dx * dz; acc[6] += dy * dy; acc[7] += dy * dz; acc[8] += dz * dz;
