@@ -105,3 +105,29 @@ class Counts(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+X_VOXELS, X_SLOPES, X_COLUMNS = 1, 2, 4
+X_MAX_RANKS = 16
+TILE_EMPTY = (GNDT_MAX_INDEX, GNDT_MAX_INDEX + 1)  # a strip range that holds no valid index
+
+
+class XchgInfo(C.Structure):
+    """gndt_xchg_info (include/gndt.h): what one rank exports to its peers, 128 bytes."""
+
+    _fields_ = [("ipc_mem", C.c_uint8 * 64), ("ptr", C.c_uint64), ("bytes", C.c_uint64), ("cap_records", C.c_uint64),
+                ("cap_halo", C.c_uint64), ("device", C.c_int32), ("pid", C.c_int32), ("what", C.c_int32), ("rank", C.c_int32),
+                ("reserved", C.c_uint8 * 16)]
+
+
+class XchgView(C.Structure):
+    """gndt_xchg_view (include/gndt.h)."""
+
+    _fields_ = [("voxels", C.c_void_p), ("slopes", C.c_void_p), ("columns", C.c_void_p),
+                ("n_voxels", C.c_uint64), ("n_slopes", C.c_uint64), ("n_columns", C.c_uint64),
+                ("world", C.c_int32), ("reserved", C.c_int32),
+                ("strip_voxels", C.c_uint64 * X_MAX_RANKS), ("strip_columns", C.c_uint64 * X_MAX_RANKS),
+                ("strip_slopes", C.c_uint64 * X_MAX_RANKS)]
+
+
+assert C.sizeof(XchgInfo) == 128

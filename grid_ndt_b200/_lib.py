@@ -5,13 +5,14 @@ import os
 import subprocess
 import sys
 
-from ._abi import Counts, Params
+from ._abi import Counts, Params, XchgInfo, XchgView
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("GNDT_LIB") or os.path.join(HERE, "libgndt.so")  # GNDT_LIB: tuning variants only
 SOURCES = [os.path.join(HERE, "csrc", f) for f in (
-    "gndt_api.cu", "gndt_device.cuh", "gndt_sort.cuh", "gndt_reduce.cuh", "gndt_label.cuh", "gndt_update.cuh")]
+    "gndt_api.cu", "gndt_device.cuh", "gndt_sort.cuh", "gndt_reduce.cuh", "gndt_label.cuh", "gndt_update.cuh",
+    "gndt_exchange.cuh")]
 HEADER = os.path.join(REPO, "include", "gndt.h")
 LOOKUP_HEADER = os.path.join(REPO, "include", "gndt_lookup.h")
 
@@ -62,6 +63,10 @@ SYMBOLS = {
     "gndt_apply_strip_offsets": (_i, [_vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _i, _vp]),
     "gndt_device_count_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "gndt_device_table_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "gndt_xchg_create": (_i, [_vp, _i, _i, _sz, _sz, _i, C.POINTER(XchgInfo)]),
+    "gndt_xchg_connect": (_i, [_vp, C.POINTER(XchgInfo), _i]),
+    "gndt_xchg_run": (_i, [_vp, _vp]),
+    "gndt_xchg_view_get": (_i, [_vp, C.POINTER(XchgView)]),
     "gndt_plan_tiles": (_i, [_vp, _vp, _sz, _sz, _i, _i, C.POINTER(C.c_int32), _vp]),
     "gndt_set_stage_timing": (_i, [_vp, _i]),
     "gndt_stage_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -18,6 +18,8 @@
 #include "gndt_reduce.cuh"
 #include "gndt_sort.cuh"
 #include "gndt_update.cuh"
+#include "gndt_exchange.cuh"
+#include <unistd.h>
 
 using namespace gndt;
 
@@ -71,6 +73,14 @@ struct gndt_handle {
   size_t zero_bytes_used = 0;
   size_t sort_tiles = 0, sort_groups = 0, red_tiles = 0, label_blocks = 0;
   Buffer f_zero;  // scratch of gndt_plan_tiles (x-column histogram)
+  // peer-mapped strip exchange (gndt_xchg_*)
+  Buffer xbuf;
+  XLayout xl = {};
+  XPeers xp = {};
+  void *x_opened[kMaxRanks] = {};  // cudaIpcOpenMemHandle mappings to close
+  int x_what = 0;
+  u32 x_epoch = 0;
+  bool x_created = false, x_connected = false;
   // state
   bool built = false;
   bool counts_valid = false;
@@ -454,8 +464,10 @@ int gndt_create(const gndt_params *params, int device, gndt_handle **out) {
 int gndt_destroy(gndt_handle *h) {
   if (!h) return GNDT_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (h->x_opened[r]) cudaIpcCloseMemHandle(h->x_opened[r]);
   Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
-                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small, &h->lookback, &h->f_zero};
+                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small, &h->lookback, &h->f_zero, &h->xbuf};
   for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
   for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -686,6 +698,146 @@ int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capac
   if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
   *dptr = static_cast<const gndt_voxel *>(h->table.p);
   if (capacity) *capacity = h->cap_voxels;
+  return GNDT_OK;
+}
+
+// ---- peer-mapped strip exchange --------------------------------------------------------
+static_assert(sizeof(gndt_xchg_info) == 128, "gndt_xchg_info is 128 bytes");
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+
+int gndt_xchg_create(gndt_handle *h, int rank, int world, size_t cap_records, size_t cap_halo_records, int what,
+                     gndt_xchg_info *mine) {
+  if (!h || !mine || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || cap_records < 1 || cap_halo_records < 1 ||
+      !(what & (GNDT_X_VOXELS | GNDT_X_SLOPES | GNDT_X_COLUMNS)))
+    return GNDT_ERR_INVALID_ARG;
+  if (cap_records > 0xFFFFFFFEull) return GNDT_ERR_CAPACITY;
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  XLayout L = {};
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.mail = carve(sizeof(XMail));
+  L.halo[0] = carve((cap_halo_records + 1) * sizeof(gndt_voxel));
+  L.halo[1] = carve((cap_halo_records + 1) * sizeof(gndt_voxel));
+  L.voxels = carve((what & GNDT_X_VOXELS) ? cap_records * sizeof(gndt_voxel) : 0);
+  L.slopes = carve((what & GNDT_X_SLOPES) ? cap_records * sizeof(gndt_slope) : 0);
+  L.columns = carve((what & GNDT_X_COLUMNS) ? cap_records * sizeof(gndt_column) : 0);
+  L.total = off;
+  L.cap_records = cap_records;
+  L.cap_halo = cap_halo_records;
+  int rc;
+  if ((rc = ensure(h, h->xbuf, L.total)) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->small, 256)) != GNDT_OK) return rc;
+  GNDT_CUDA(h, cudaMemset(h->xbuf.p, 0, sizeof(XMail)));
+  GNDT_CUDA(h, cudaMemset(static_cast<char *>(h->small.p) + 160, 0, 64));
+  h->xl = L;
+  h->xp = XPeers{};
+  h->xp.rank = rank;
+  h->xp.world = world;
+  h->x_what = what;
+  h->x_epoch = 0;
+  h->x_created = true;
+  h->x_connected = false;
+  memset(mine, 0, sizeof(*mine));
+  cudaIpcMemHandle_t ipc;
+  GNDT_CUDA(h, cudaIpcGetMemHandle(&ipc, h->xbuf.p));
+  memcpy(mine->ipc_mem, &ipc, 64);
+  mine->ptr = (uint64_t)(uintptr_t)h->xbuf.p;
+  mine->bytes = L.total;
+  mine->cap_records = cap_records;
+  mine->cap_halo = cap_halo_records;
+  mine->device = h->device;
+  mine->pid = (int32_t)getpid();
+  mine->what = what;
+  mine->rank = rank;
+  return GNDT_OK;
+}
+
+int gndt_xchg_connect(gndt_handle *h, const gndt_xchg_info *all, int world) {
+  if (!h || !all) return GNDT_ERR_INVALID_ARG;
+  if (!h->x_created || world != h->xp.world) { h->err = "gndt_xchg_connect: create the exchange first / world mismatch"; return GNDT_ERR_STATE; }
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  for (int r = 0; r < world; ++r) {
+    const gndt_xchg_info &in = all[r];
+    if (in.rank != r || in.bytes != h->xl.total || in.cap_records != h->xl.cap_records || in.cap_halo != h->xl.cap_halo || in.what != h->x_what) {
+      h->err = "gndt_xchg_connect: rank " + std::to_string(r) + " has a different exchange layout";
+      return GNDT_ERR_INVALID_ARG;
+    }
+    if (r == h->xp.rank) { h->xp.buf[r] = static_cast<unsigned char *>(h->xbuf.p); continue; }
+    if (in.pid == (int32_t)getpid()) {  // same process: plain peer access
+      if (in.device != h->device) {
+        int can = 0;
+        GNDT_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, in.device));
+        if (!can) { h->err = "no peer access between devices " + std::to_string(h->device) + " and " + std::to_string(in.device); return GNDT_ERR_CUDA; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(in.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = cudaGetErrorString(e); return GNDT_ERR_CUDA; }
+        cudaGetLastError();
+      }
+      h->xp.buf[r] = reinterpret_cast<unsigned char *>((uintptr_t)in.ptr);
+    } else {  // another process: map its buffer
+      cudaIpcMemHandle_t ipc;
+      memcpy(&ipc, in.ipc_mem, 64);
+      void *p = nullptr;
+      GNDT_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->x_opened[r] = p;
+      h->xp.buf[r] = static_cast<unsigned char *>(p);
+    }
+  }
+  h->x_connected = true;
+  return GNDT_OK;
+}
+
+int gndt_xchg_run(gndt_handle *h, void *stream) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
+  if (!h->x_connected) { h->err = "gndt_xchg_run: exchange not connected"; return GNDT_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  const u32 epoch = ++h->x_epoch;
+  const XPeers &X = h->xp;
+  const XLayout &L = h->xl;
+  int *have = reinterpret_cast<int *>(static_cast<char *>(h->small.p) + 160);
+  u32 *done_counter = reinterpret_cast<u32 *>(static_cast<char *>(h->small.p) + 192);
+  const DevParams dp = make_dev(h, h->params, h->cap_voxels);
+  unsigned char *mine = X.buf[X.rank];
+  xchg_publish_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch);
+  xchg_halo_send_kernel<<<2, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_column *)h->columns.p, h->row_start,
+                                           h->row_end, X, L, epoch);
+  xchg_halo_wait_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch, have);
+  xchg_halo_edges_kernel<<<grid_for(h, h->cap_voxels, 256, 4), 256, 0, st>>>(
+      h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p, reinterpret_cast<const gndt_voxel *>(mine + L.halo[0]),
+      reinterpret_cast<const gndt_voxel *>(mine + L.halo[1]), have, dp);
+  xchg_push_kernel<<<h->sm_count, 512, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_slope *)h->slopes.p,
+                                                (const gndt_column *)h->columns.p, X, L, h->x_what, epoch, done_counter);
+  xchg_wait_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch);
+  h->launches += 6;
+  h->counts_valid = false;
+  h->last_stream = st;
+  GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
+int gndt_xchg_view_get(gndt_handle *h, gndt_xchg_view *out) {
+  if (!h || !out) return GNDT_ERR_INVALID_ARG;
+  if (!h->x_connected || h->x_epoch == 0) { h->err = "gndt_xchg_view_get: no exchange has run"; return GNDT_ERR_STATE; }
+  int rc = sync_counts(h);  // synchronises the stream, surfaces watchdog / capacity errors
+  if (rc != GNDT_OK) return rc;
+  XMail mail;
+  GNDT_CUDA(h, cudaMemcpy(&mail, h->xp.buf[h->xp.rank] + h->xl.mail, sizeof(XMail), cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(*out));
+  unsigned char *mine = h->xp.buf[h->xp.rank];
+  out->voxels = (h->x_what & GNDT_X_VOXELS) ? reinterpret_cast<const gndt_voxel *>(mine + h->xl.voxels) : nullptr;
+  out->slopes = (h->x_what & GNDT_X_SLOPES) ? reinterpret_cast<const gndt_slope *>(mine + h->xl.slopes) : nullptr;
+  out->columns = (h->x_what & GNDT_X_COLUMNS) ? reinterpret_cast<const gndt_column *>(mine + h->xl.columns) : nullptr;
+  out->world = h->xp.world;
+  for (int r = 0; r < h->xp.world; ++r) {
+    if (mail.counts[r][3] != h->x_epoch || mail.done[r] != h->x_epoch) { h->err = "exchange incomplete (epoch mismatch)"; return GNDT_ERR_INTERNAL; }
+    out->strip_voxels[r] = mail.counts[r][0];
+    out->strip_columns[r] = mail.counts[r][1];
+    out->strip_slopes[r] = mail.counts[r][2];
+    out->n_voxels += mail.counts[r][0];
+    out->n_columns += mail.counts[r][1];
+    out->n_slopes += mail.counts[r][2];
+  }
   return GNDT_OK;
 }
 

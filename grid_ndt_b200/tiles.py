@@ -1,5 +1,12 @@
 """Multi-GPU map build: one x strip of the map per GPU of a single box, one process per GPU.
 
+Default exchange ("native"): the halo rows and the gather of the finished tables go through
+peer-mapped memory inside libgndt.so (gndt_xchg_*, csrc/gndt_exchange.cuh): no NCCL kernel, no
+host synchronisation for the strip sizes, strip-local indices made global while the records are
+pushed.  torch.distributed only carries the 128-byte buffer handles between the ranks once, at
+construction.  The older NCCL point-to-point form (exchange="nccl") is kept for comparison and
+is what the rest of this docstring describes.
+
 Everything up to and including the surface labels depends only on the points of one x-y
 column, so strips need no exchange while they are built.  The only cross-
 strip dependence is the forward/back reachability of the first and last x row of a strip, so
@@ -25,7 +32,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._abi import VOXEL_DTYPE
+from . import _abi
+from ._abi import COLUMN_DTYPE, SLOPE_DTYPE, VOXEL_DTYPE, XchgInfo, XchgView
 from ._lib import lib
 from .builder import TwoDmap, _check
 
@@ -41,10 +49,33 @@ class _Slot:
         self.device = torch.device("cuda", self.map._device)
         self.stream = torch.cuda.Stream(self.device) if own_stream else None
         self.counts = torch.zeros(world * 4, dtype=torch.int32, device=self.device)
-        self.halo = torch.zeros(4 * (halo_records + 1) * REC, dtype=torch.uint8, device=self.device)
+        self.halo = torch.zeros(4 * (halo_records + 1) * REC, dtype=torch.uint8, device=self.device) if halo_records else None
         self.table = None
+        self.g_slopes = self.g_columns = None
         self.offsets = None
         self.strip_counts = None
+
+
+class Gathered(tuple):
+    """Result of collect(): unpacks as (voxel table or None, offsets) like before, and carries the
+    gathered slope / column tables and the per-strip counts as attributes."""
+
+    def __new__(cls, table, offsets, **kw):
+        obj = super().__new__(cls, (table, offsets))
+        obj.__dict__.update(kw)
+        return obj
+
+
+def allgather_bytes(blob: bytes, world: int, group=None, device=None) -> list:
+    """Every rank's fixed-size byte blob, in rank order (the one collective of the native
+    exchange: buffer handles at construction).  CPU tensors with gloo, CUDA tensors with NCCL."""
+    t = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world * len(blob), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    raw = out.cpu().numpy().tobytes()
+    return [raw[i * len(blob):(i + 1) * len(blob)] for i in range(world)]
 
 
 class TiledTwoDmap:
@@ -52,12 +83,32 @@ class TiledTwoDmap:
     keeps columns with cuts[r] <= cx < cuts[r+1] (gndt_params.tile_lo/hi)."""
 
     def __init__(self, res, zres, interval, rank: int, world: int, device: Optional[int] = None, group=None,
-                 halo_records: int = 32768, depth: int = 1):
+                 halo_records: int = 32768, depth: int = 1, exchange: str = "native", gather=("voxels", "slopes", "columns"),
+                 capacity: int = 8_000_000):
+        """exchange: "native" (peer-mapped memory inside libgndt.so) or "nccl" (point-to-point).
+        gather: which tables of the whole map every rank ends up with (native only; the planner reads
+        slopes + columns).  capacity: voxels of the WHOLE map the gathered tables can hold (native)."""
         self.rank, self.world, self.group = rank, world, group
         self.halo_records = halo_records  # capacity of one halo row (records); overflow is reported, not truncated
-        self.slots = [_Slot(res, zres, interval, world, device, halo_records, own_stream=depth > 1) for _ in range(depth)]
+        self.exchange = exchange if world > 1 else "nccl"  # one strip: nothing to exchange
+        self.what = sum({"voxels": _abi.X_VOXELS, "slopes": _abi.X_SLOPES, "columns": _abi.X_COLUMNS}[g] for g in gather)
+        self.slots = [_Slot(res, zres, interval, world, device, halo_records if self.exchange == "nccl" else 0, own_stream=depth > 1)
+                      for _ in range(depth)]
         self.gather_group = group
-        if depth > 1 and world > 1:
+        if self.exchange == "native":
+            L = lib()
+            infos = b""
+            for s in self.slots:
+                mine = XchgInfo()
+                _check(s.map._h, L.gndt_xchg_create(s.map._h, rank, world, int(capacity), int(halo_records), self.what, C.byref(mine)))
+                infos += bytes(mine)
+            every = allgather_bytes(infos, world, group, self.slots[0].device if dist.get_backend(group) == "nccl" else None)
+            for k, s in enumerate(self.slots):
+                arr = (XchgInfo * world)()
+                for r in range(world):
+                    C.memmove(C.byref(arr[r]), every[r][k * 128:(k + 1) * 128], 128)
+                _check(s.map._h, L.gndt_xchg_connect(s.map._h, arr, world))
+        elif depth > 1 and world > 1:
             # second communicator: the record gather of build i must not queue behind the halo /
             # size exchange of build i+1 (collective: every rank constructs its TiledTwoDmap)
             self.gather_group = dist.new_group(ranks=list(range(world))) if group is None else dist.new_group(
@@ -116,7 +167,10 @@ class TiledTwoDmap:
             if origin is not None:
                 m.setCloudFirst(origin)
             if cuts is not None and filter_points:
-                m.setTile(int(cuts[self.rank]), int(cuts[self.rank + 1]))
+                lo, hi = int(cuts[self.rank]), int(cuts[self.rank + 1])
+                # an empty strip (equal cuts: one x row holds more than its share of the points)
+                # must keep NOTHING; lo >= hi would mean "filter off"
+                m.setTile(*((lo, hi) if lo < hi else _abi.TILE_EMPTY))
             else:
                 m.setTile(0, 0)
         stream = s.stream if s.stream is not None else torch.cuda.current_stream(s.device)
@@ -129,6 +183,11 @@ class TiledTwoDmap:
             else:
                 m.uniformDivision(cloud)
                 m.create2DMap(demand, stream=st)
+            if self.exchange == "native":
+                # halo rows, strip sizes, gather, index fix-up: all inside the library, all on this stream
+                _check(m._h, L.gndt_xchg_run(m._h, st))
+                self._inflight.append(s)
+                return s
             slot_b = (self.halo_records + 1) * REC
             send_first, send_last, recv_prev, recv_next = (s.halo[i * slot_b:(i + 1) * slot_b] for i in range(4))
             _check(m._h, L.gndt_halo_pack(m._h, send_first.data_ptr(), send_last.data_ptr(), self.halo_records, st))
@@ -162,6 +221,21 @@ class TiledTwoDmap:
         s = self._inflight.popleft()
         m, L = s.map, lib()
         stream = s.stream if s.stream is not None else torch.cuda.current_stream(s.device)
+        if self.exchange == "native":
+            v = XchgView()
+            _check(m._h, L.gndt_xchg_view_get(m._h, C.byref(v)))  # synchronises this builder's stream only
+            w = self.world
+            sv = np.array(v.strip_voxels[:w], np.int64)
+            s.strip_counts = np.stack([sv, np.array(v.strip_columns[:w], np.int64), np.array(v.strip_slopes[:w], np.int64),
+                                       np.zeros(w, np.int64)], 1)
+            s.offsets = np.concatenate([[0], np.cumsum(sv)]).astype(np.uint64)
+            view = lambda ptr, n, rec: (_as_tensor(ptr, max(int(n), 1) * rec, s.device)[: int(n) * rec].view(-1, rec) if ptr else None)
+            s.table = view(v.voxels, v.n_voxels, REC)
+            s.g_slopes = view(v.slopes, v.n_slopes, SLOPE_DTYPE.itemsize)
+            s.g_columns = view(v.columns, v.n_columns, COLUMN_DTYPE.itemsize)
+            self._last = s
+            return Gathered(s.table, s.offsets, slopes=s.g_slopes, columns=s.g_columns, strip_counts=s.strip_counts,
+                            n_voxels=int(v.n_voxels), n_slopes=int(v.n_slopes), n_columns=int(v.n_columns))
         with torch.cuda.stream(stream):
             st = stream.cuda_stream
             counts4 = s.counts.cpu().numpy().astype(np.int64).reshape(self.world, 4)  # {voxels, columns, slopes, fitted}
@@ -226,39 +300,21 @@ class TiledTwoDmap:
                 s.stream.synchronize()
         torch.cuda.current_stream(self.device).synchronize()
 
-    def gathered_numpy(self) -> np.ndarray:
+    def gathered_numpy(self, which: str = "voxels") -> np.ndarray:
+        """The gathered voxel (or, native exchange, slope / column) table of the last collected build."""
         self.synchronize()
         s = self._last
+        if self.exchange == "native":
+            t, dt = {"voxels": (s.table, VOXEL_DTYPE), "slopes": (s.g_slopes, SLOPE_DTYPE), "columns": (s.g_columns, COLUMN_DTYPE)}[which]
+            if t is None:
+                raise RuntimeError(f"{which} were not gathered (gather=...)")
+            return t.cpu().numpy().reshape(-1).view(dt)
         total = int(s.offsets[-1])
         return s.table[: total * REC].cpu().numpy().view(VOXEL_DTYPE).reshape(-1)
 
     def close(self):
         for s in self.slots:
             s.map.close()
-
-
-def allgather_strips(local: torch.Tensor, world: int, group=None):
-    """All-gather variable-length strip tables (flat uint8, 96 B records) into one compact
-    table in rank order with collectives only (sizes, then padded records).  Device-agnostic:
-    NCCL on CUDA tensors, gloo on CPU tensors — the CPU form is what the world_size-2 unit test
-    exercises; TiledTwoDmap uses the unpadded point-to-point form of the same exchange.
-    Returns (table, offsets)."""
-    dev = local.device
-    n = local.numel() // REC
-    cnt = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(cnt, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
-    counts = cnt.cpu().numpy()
-    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    total, vmax = int(offsets[-1]), max(int(counts.max()), 1)
-    send = torch.zeros(vmax * REC, dtype=torch.uint8, device=dev)
-    send[: n * REC] = local
-    recv = torch.empty(world * vmax * REC, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    table = torch.empty(max(total, 1) * REC, dtype=torch.uint8, device=dev)
-    for r in range(world):
-        c = int(counts[r])
-        table[offsets[r] * REC: (offsets[r] + c) * REC] = recv[r * vmax * REC: r * vmax * REC + c * REC]
-    return table, offsets
 
 
 def _as_tensor(ptr: int, nbytes: int, device) -> torch.Tensor:

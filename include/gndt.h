@@ -72,7 +72,9 @@ typedef struct gndt_params {
                                   1 = divide by n (computeCovarianceMatrixNormalized)       */
   int32_t tile_lo;             /* multi-GPU x strip: keep columns with tile_lo <= cx <      */
   int32_t tile_hi;             /*   tile_hi, cx = contiguous signed x index (sx>0?sx-1:sx). */
-                               /*   tile_lo >= tile_hi disables the filter (single GPU).    */
+                               /*   tile_lo >= tile_hi disables the filter (single GPU).  An  */
+                               /*   EMPTY strip is any range without a valid index, e.g.     */
+                               /*   [GNDT_MAX_INDEX, GNDT_MAX_INDEX + 1).                     */
   uint64_t max_voxels;         /* capacity of the device voxel table; 0 = number of points  */
 } gndt_params;
 
@@ -229,6 +231,49 @@ int gndt_apply_strip_offsets(gndt_handle *h, gndt_voxel *table, const uint64_t *
  * count of the last build, and of the table with its capacity in records. */
 int gndt_device_count_ptr(gndt_handle *h, const uint32_t **d_n_voxels); /* -> {n_voxels, n_columns, n_slopes, n_fitted} */
 int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capacity);
+
+/*
+ * Strip exchange through peer-mapped memory: the halo rows and the gather of the finished
+ * tables without NCCL and without a host round trip (sizes stay on the device).  Every rank
+ * (one handle per GPU; ranks may be threads of one process or separate processes) creates an
+ * exchange buffer and exports it as a gndt_xchg_info blob; the caller moves the blobs between
+ * ranks by any means (MPI, torch.distributed, a pipe) and hands all of them to
+ * gndt_xchg_connect.  After each gndt_build / gndt_update of the strips, gndt_xchg_run
+ * (stream-ordered, every rank calls it once per build) leaves on EVERY rank the tables of the
+ * whole map, strips concatenated in rank order, indices global:
+ *   - forward / back reach bits of strip-boundary rows completed from the neighbour strip
+ *     (the countLRFB neighbours of include/map2D.h:219-253 that live on another GPU); empty
+ *     strips are skipped, their neighbours exchange rows with each other
+ *   - `what` selects the tables to gather: the planner reads Slopes and Cells
+ *     (GNDT_X_SLOPES | GNDT_X_COLUMNS, 80 B per voxel instead of 176)
+ * cap_records bounds the voxels of the WHOLE map, cap_halo_records those of one x row.
+ */
+#define GNDT_X_VOXELS 1
+#define GNDT_X_SLOPES 2
+#define GNDT_X_COLUMNS 4
+#define GNDT_X_MAX_RANKS 16
+typedef struct gndt_xchg_info {
+  uint8_t ipc_mem[64];   /* cudaIpcMemHandle_t of the exchange buffer                   */
+  uint64_t ptr;          /* its address in the exporting process (same-process peers)   */
+  uint64_t bytes, cap_records, cap_halo;
+  int32_t device, pid, what, rank;
+  uint8_t reserved[16];
+} gndt_xchg_info;
+typedef struct gndt_xchg_view {
+  const gndt_voxel *voxels;    /* device pointers into this rank's gathered tables (NULL if   */
+  const gndt_slope *slopes;    /* not selected), valid until the next gndt_xchg_run           */
+  const gndt_column *columns;
+  uint64_t n_voxels, n_slopes, n_columns;
+  int32_t world, reserved;
+  uint64_t strip_voxels[GNDT_X_MAX_RANKS], strip_columns[GNDT_X_MAX_RANKS], strip_slopes[GNDT_X_MAX_RANKS];
+} gndt_xchg_view;
+int gndt_xchg_create(gndt_handle *h, int rank, int world, size_t cap_records, size_t cap_halo_records, int what,
+                     gndt_xchg_info *mine);
+int gndt_xchg_connect(gndt_handle *h, const gndt_xchg_info *all, int world);
+int gndt_xchg_run(gndt_handle *h, void *stream);
+/* Synchronises the exchange stream; fails with GNDT_ERR_CAPACITY if the map outgrew
+ * cap_records / a row outgrew cap_halo_records, GNDT_ERR_INTERNAL if a peer never showed up. */
+int gndt_xchg_view_get(gndt_handle *h, gndt_xchg_view *out);
 
 /*
  * Balanced x strips for `ntiles` GPUs: cuts[0..ntiles] in contiguous signed x index

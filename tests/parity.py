@@ -182,6 +182,10 @@ def compare(gpu_vox, gpu_cols, gpu_slopes, gpu_counts, o32, o64, params, check_r
         if rb.size != rep["reach_mismatch_threshold_adjacent"]:
             fail(f"reach bits: {rb.size - rep['reach_mismatch_threshold_adjacent']} mismatches are NOT threshold-adjacent")
 
+    # column slope_begin / slope_count follow from the labels: with identical labels they must be identical
+    if rep["label_mismatch"] == 0 and (rep.get("col_slope_begin_mismatch", 0) or rep.get("col_slope_count_mismatch", 0)):
+        fail(f"column slope_begin/slope_count differ ({rep['col_slope_begin_mismatch']}/{rep['col_slope_count_mismatch']}) although all labels agree")
+
     # ---- slope table consistency with the voxel table
     is_slope = (gpu_vox["flags"] & _abi.F_SLOPE) != 0
     if len(gpu_slopes) != int(is_slope.sum()):
@@ -193,6 +197,35 @@ def compare(gpu_vox, gpu_cols, gpu_slopes, gpu_counts, o32, o64, params, check_r
                 and np.array_equal(gpu_slopes["rough"], gpu_vox["rough"][idx]) and np.array_equal(gpu_slopes["flags"], gpu_vox["flags"][idx])):
             fail("slope table does not mirror the voxel table")
     return rep
+
+
+def compare_gathered(vox, cols, slopes, o32, o64, params, check_reach=True):
+    """The same bar for a map assembled from several GPUs' strips: counts are derived from the
+    gathered tables themselves (no strip may have lost or duplicated a record)."""
+    counts = {"n_binned": int(vox["count"].sum()), "n_dropped": o32.counts["n_dropped"], "n_outside_tile": 0,
+              "n_columns": len(cols), "n_voxels": len(vox), "n_fitted": int(((vox["flags"] & _abi.F_FITTED) != 0).sum()),
+              "n_slopes": len(slopes)}
+    return compare(vox, cols, slopes, counts, o32, o64, params, check_reach=check_reach)
+
+
+def assemble_strips(strips):
+    """Host statement of what the device-side push (csrc/gndt_exchange.cuh, xchg_push_kernel) does
+    to strip-local indices: strips = [(voxels, columns)] in rank order -> (voxels, columns) of the
+    whole map.  voxel.column += columns before, voxel.slope += slopes before (unless none),
+    column.voxel_begin += voxels before, column.slope_begin += slopes before."""
+    vox_off = col_off = slope_off = 0
+    vs, cs = [], []
+    for v, c in strips:
+        v, c = v.copy(), c.copy()
+        v["column"] += np.uint32(col_off)
+        has = v["slope"] != 0xFFFFFFFF
+        v["slope"][has] += np.uint32(slope_off)
+        c["voxel_begin"] += np.uint32(vox_off)
+        c["slope_begin"] += np.uint32(slope_off)
+        vox_off, col_off, slope_off = vox_off + len(v), col_off + len(c), slope_off + int(has.sum())
+        vs.append(v)
+        cs.append(c)
+    return np.concatenate(vs), np.concatenate(cs)
 
 
 def _angle(n1, n2):

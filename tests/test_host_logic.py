@@ -54,15 +54,20 @@ def test_tile_filter_partitions_the_map():
 
 
 _WORKER = r"""
-import os, sys
+import os, pickle, sys
 sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
-from grid_ndt_b200 import synthetic
-from grid_ndt_b200._abi import default_params, VOXEL_DTYPE
-from grid_ndt_b200.tiles import allgather_strips
+from grid_ndt_b200 import synthetic, _abi
+from grid_ndt_b200._abi import default_params
+from grid_ndt_b200.tiles import allgather_bytes
 from oracle import oracle as O
+from tests import parity
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
+# the one collective of the native exchange: fixed-size buffer handles, in rank order
+blob = bytes([rank]) * 128
+every = allgather_bytes(blob, world)
+assert every == [bytes([r]) * 128 for r in range(world)], every
 cloud = synthetic.cfg2(120_000, scale=0.12)
 def params(lo, hi):
     p = default_params(0.2, 0.1, 0.08); p.origin_is_first_point = 0
@@ -72,25 +77,30 @@ def params(lo, hi):
 full = O.oracle_build(cloud, params(0, 0))
 cx = np.where(full.voxels["sx"] > 0, full.voxels["sx"] - 1, full.voxels["sx"])
 cut = int(np.quantile(cx, 0.4))
-cuts = [-40000, cut, 40000]
-mine = O.oracle_build(cloud, params(cuts[rank], cuts[rank + 1]))
-local = torch.from_numpy(mine.voxels.view(np.uint8).copy())
-table, offsets = allgather_strips(local, world)
-got = table[: int(offsets[-1]) * 96].numpy().view(VOXEL_DTYPE)
-assert int(offsets[-1]) == len(full.voxels), (offsets, len(full.voxels))
-assert offsets[rank + 1] - offsets[rank] == len(mine.voxels)
-for f in ("sx", "sy", "sz", "count", "first_index", "mean", "scatter", "evals", "rough"):
-    assert np.array_equal(got[f], full.voxels[f]), f
-assert np.array_equal(got["flags"] & 0x0F, full.voxels["flags"] & 0x0F)
+for cuts in ([-32768, cut, 32768], [-32768, -32768, 32768]):   # the second: strip 0 is EMPTY
+    lo, hi = cuts[rank], cuts[rank + 1]
+    if lo >= hi: lo, hi = _abi.TILE_EMPTY                       # equal cuts must keep nothing (lo >= hi = filter off)
+    mine = O.oracle_build(cloud, params(lo, hi))
+    if cuts[rank] >= cuts[rank + 1]: assert len(mine.voxels) == 0
+    got = [None] * world
+    dist.all_gather_object(got, (mine.voxels, mine.columns))
+    vox, cols = parity.assemble_strips(got)
+    assert len(vox) == len(full.voxels) and len(cols) == len(full.columns)
+    for f in ("sx", "sy", "sz", "count", "first_index", "mean", "scatter", "evals", "rough", "column", "slope"):
+        assert np.array_equal(vox[f], full.voxels[f]), f
+    assert np.array_equal(vox["flags"] & 0x10F, full.voxels["flags"] & 0x10F)
+    for f in ("sx", "sy", "first_index", "voxel_begin", "voxel_count", "slope_begin", "slope_count"):
+        assert np.array_equal(cols[f], full.columns[f]), f
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
 
 
-def test_strip_allgather_world2_gloo(tmp_path):
-    """The N>1 host path (sizes all-gather, padded record all-gather, compaction) with two
-    gloo ranks on CPU; strips come from the oracle so no GPU is involved."""
+def test_strips_world2_gloo(tmp_path):
+    """The N>1 host logic with two gloo ranks on CPU: the handle exchange of the native strip
+    exchange, the empty-strip rule, and the index fix-up rule of the device-side push (stated on
+    the host in tests/parity.assemble_strips); strips come from the oracle, no GPU involved."""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER.format(root=ROOT))
     port = 29500 + (os.getpid() % 2000)
