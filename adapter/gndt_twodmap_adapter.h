@@ -17,6 +17,10 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
+#include <deque>
+#include <list>
+#include <map>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -132,6 +136,116 @@ struct CellIndex {
     if (!c) return NULL;
     std::map<int, daysun::Slope *, CmpByKeyUD>::iterator it = c->map_slope.find(sz);
     return it == c->map_slope.end() ? NULL : it->second;
+  }
+};
+
+// The traversability graph of gndt_build_edges (CSR over the slope table) bound to the host
+// Slope objects: AccessibleNeighborsFast returns the list TwoDmap::AccessibleNeighbors
+// (map2D.h:530-548) returns — same Slopes, same order — without building a key string,
+// searching map_cell or evaluating countAngle: a slice of an integer array.
+struct SlopeGraph {
+  std::vector<daysun::Slope *> slope;                 // slope-table index -> host object
+  std::map<const daysun::Slope *, unsigned> index;    // host object -> slope-table index
+  std::vector<unsigned char> last_in_cell;            // 1: no Slope above it in its Cell
+  const uint32_t *offsets, *targets;
+
+  SlopeGraph(daysun::TwoDmap &m, const gndt_column *cols, size_t n_cols, size_t n_slopes, const uint32_t *off, const uint32_t *tgt)
+      : slope(n_slopes, (daysun::Slope *)NULL), last_in_cell(n_slopes, 0), offsets(off), targets(tgt) {
+    for (size_t c = 0; c < n_cols; ++c) {
+      std::map<std::string, daysun::Cell *>::iterator it = m.map_cell.find(morton_key(cols[c].sx, cols[c].sy));
+      if (it == m.map_cell.end()) continue;
+      unsigned k = cols[c].slope_begin;  // Cell::map_slope iterates in ascending z = slope-table order
+      for (std::map<int, daysun::Slope *, CmpByKeyUD>::iterator sit = it->second->map_slope.begin(); sit != it->second->map_slope.end(); ++sit, ++k)
+        if (k < n_slopes) { slope[k] = sit->second; index[sit->second] = k; }
+      if (cols[c].slope_count) last_in_cell[cols[c].slope_begin + cols[c].slope_count - 1] = 1;
+    }
+  }
+  std::list<daysun::Slope *> AccessibleNeighborsFast(daysun::Slope *s) const {
+    std::list<daysun::Slope *> out;
+    std::map<const daysun::Slope *, unsigned>::const_iterator it = index.find(s);
+    if (it == index.end()) return out;
+    for (uint32_t e = offsets[it->second]; e < offsets[it->second + 1]; ++e) out.push_back(slope[targets[e]]);
+    return out;
+  }
+
+  // TwoDmap::CollisionCheck (map2D.h:351-411) on slope-table indices; same control flow, the
+  // reference's expressions kept verbatim (including `(a < b) + 2*r`, a bool plus a float, :385).
+  bool collides(unsigned i, int n, RobotSphere &robot, std::vector<unsigned> &mark, unsigned &stamp) const {
+    daysun::Slope *s = slope[i];
+    const float r = robot.getRobotR();
+    if (s->up == true) return true;
+    std::vector<unsigned> all(1, i), now(1, i), add;
+    ++stamp;
+    mark[i] = stamp;  // isContainedQ(*, allSlope): identity of (morton_xy, morton_z) = identity of the Slope
+    while (n > 0) {
+      for (size_t a = 0; a < now.size(); ++a)
+        for (uint32_t e = offsets[now[a]]; e < offsets[now[a] + 1]; ++e) {
+          const unsigned t = targets[e];
+          if (mark[t] != stamp) { mark[t] = stamp; add.push_back(t); all.push_back(t); }
+        }
+      --n;
+      now.swap(add);
+      add.clear();
+    }
+    for (size_t a = 0; a < all.size(); ++a) {
+      daysun::Slope *o = slope[all[a]];
+      if ((o->mean(2) < s->mean(2)) && o->up == true) return true;
+      if ((o->mean(2) > s->mean(2)) && (((o->mean(2) < s->mean(2)) + 2 * r)) && (o->mean(2) - s->mean(2) > robot.getReachableHeight())) return true;
+    }
+    if (!last_in_cell[i]) {  // the next Slope above in the same Cell (:397-407)
+      daysun::Slope *up = slope[i + 1];
+      return (up->mean(2) < s->mean(2) + 2 * r) && (up->mean(2) - s->mean(2) > robot.getReachableHeight());
+    }
+    return false;
+  }
+
+  // TwoDmap::computeCost, demand "slope" (map2D.h:1285-1350): the goal-seeded FIFO relaxation
+  // of Slope::h, with the graph for the neighbour lists and flags for the list-membership scans
+  // (isContainedQ is O(list) per call in the reference).  Same visiting order, same float
+  // expressions, hence the same h on every Slope.  Returns the number of traversable Slopes
+  // ("traversability slopes", :1387), or -1 when the goal is not on a Slope (:1302).
+  long computeCostFast(daysun::TwoDmap &m, octomath::Vector3 goal, RobotSphere &robot) const {
+    std::string key;
+    int z;
+    m.transMortonXYZ(goal, key, z);
+    std::map<std::string, daysun::Cell *>::iterator it = m.map_cell.find(key);
+    if (it == m.map_cell.end()) return 0;  // the reference falls through with an empty queue
+    std::map<int, daysun::Slope *, CmpByKeyUD>::iterator ss = it->second->map_slope.find(z);
+    if (ss == it->second->map_slope.end()) return -1;
+    const unsigned g = index.find(ss->second)->second;
+    slope[g]->h = 0;
+    const int n = (ceil(2 * robot.getRobotR() / m.getGridLen()) - 1) / 2;
+    std::vector<unsigned char> in_q(slope.size(), 0), in_closed(slope.size(), 0), in_trav(slope.size(), 0);
+    std::vector<unsigned> mark(slope.size(), 0);
+    unsigned stamp = 0;
+    std::deque<unsigned> Q(1, g);
+    in_q[g] = 1;
+    long n_trav = 0;
+    while (!Q.empty()) {
+      const unsigned cur = Q.front();
+      daysun::Slope *c = slope[cur];
+      if (!collides(cur, n, robot, mark, stamp)) {
+        for (uint32_t e = offsets[cur]; e < offsets[cur + 1]; ++e) {
+          const unsigned t = targets[e];
+          daysun::Slope *nb = slope[t];
+          if (nb->up == true) {
+            nb->h = FLT_MAX;
+            in_closed[t] = 1;
+          } else if (nb->h > c->h + m.TravelCost(c->mean, nb->mean, goal(2))) {
+            nb->h = c->h + m.TravelCost(c->mean, nb->mean, goal(2));
+            if (!in_q[t] && !in_closed[t] && !in_trav[t]) { Q.push_back(t); in_q[t] = 1; }
+          }
+        }
+        in_trav[cur] = 1;
+        ++n_trav;
+      } else {
+        c->h = FLT_MAX;
+        in_closed[cur] = 1;
+      }
+      Q.pop_front();
+      in_q[cur] = 0;
+    }
+    return n_trav;
   }
 };
 

@@ -7,22 +7,25 @@
 A "step" is one complete map build (bounds -> partition -> fit -> labels -> edges) of one
 synthetic cloud.  N = 1: BASELINE.json configs[1] (cfg2: 10 M points, multi-level bridge /
 underpass scene, 0.2 m cells).  N > 1: one x strip per GPU, each strip one cfg2 scene
-(weak scaling: 10 M points per GPU), thin halo rows swapped between neighbour strips and
-the finished strips gathered over NCCL inside the timed region.
+(weak scaling: 10 M points per GPU); the thin halo rows and the gather of the finished
+Slope + Cell tables (what the host planner reads) go through peer-mapped memory inside
+libgndt.so (csrc/gndt_exchange.cuh), inside the timed region.  NCCL only carries the
+barrier / max-over-ranks of the timing itself.
 
-`value`   : points/s, device-timed with CUDA events, inputs resident in HBM, max over ranks,
-            K back-to-back builds with two in flight on separate streams (a second build fills
-            the SMs idle in the last wave of every kernel; at N > 1 it also hides the NVLink
-            gather).  `serial_ms_per_step` is the device time of one build run alone.
-`e2e`     : the same metric through the public TwoDmap call with PINNED HOST input, the
-            host->device copy of the cloud and the device->host copy of the voxel / slope /
-            column tables inside the timed region, every step.  At N = 1 the headline e2e
-            runs two builders deep (CloudPipeline: upload of cloud i+1 overlaps build and
-            read-back of cloud i), at N > 1 the two-deep strip pipeline with host input;
-            the one-at-a-time figure is `serial_ms_per_step`.
-`roofline`: algorithmic bytes of one build (16 B per point read once + 96 B per voxel
-            record written once) / device time per build, against the
-            measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`value`         : points/s, device-timed with CUDA events, inputs resident in HBM, max over
+                  ranks, K back-to-back builds with two (N > 1: three) in flight on separate
+                  streams.  `value_latency` / `serial_ms_per_step`: one build at a time.
+`e2e`           : the same metric through the public TwoDmap call with PINNED HOST input, the
+                  host->device copy of the cloud and the device->host copy of the result
+                  tables inside the timed region, every step (N > 1: every rank uploads its
+                  cloud, rank 0 reads back the gathered Slope + Cell tables of the WHOLE map).
+`roofline`      : algorithmic bytes of one build (16 B per point read once + 96 B per voxel
+                  record written once) / device time of one build alone,
+                  against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+N > 1 adds, outside the timed region: `parity` (a 2 M-point strip build + exchange held to
+the full parity bar against the oracle on rank 0; the run fails on any unexplained mismatch)
+and `target_cfg3` (the north-star case: ONE 50 M-point cloud at 0.1 m cells, strong-scaled
+over the N strips, both input conventions).
 """
 import argparse
 import json
@@ -41,9 +44,11 @@ CFG = "cfg2"
 POINTS_PER_GPU = 10_000_000
 GRID_LEN, Z_LEN, INTERVAL = 0.2, 0.1, 0.08
 SCENE_W = 120.0
-DEPTH = int(os.environ.get("GNDT_BENCH_DEPTH", "3"))  # N > 1: builds in flight (4 GPUs: 3 -> 0.99 ms, 2 -> 1.07 ms per step)
-REF_STEP_POINTS = 1_000_000      # --impl reference: points per timed step (bounded sample; smaller samples flatter the CPU code)
+DEPTH = int(os.environ.get("GNDT_BENCH_DEPTH", "3"))  # N > 1: builds in flight
+REF_STEP_POINTS = 1_000_000      # --impl reference: points per timed step (bounded sample)
 CPU_BASELINE_POINTS = 4_000_000  # cpu_baseline leg of the default run
+TARGET_POINTS = int(os.environ.get("GNDT_BENCH_TARGET_POINTS", "50000000"))  # north-star cloud (N > 1); 0 disables
+WORKLOAD = "cfg2 multi-level bridge/underpass scene, 10M points per GPU, 0.2 m cells, z 0.1 m, slope_interval 0.08, demand slope (BASELINE configs[1])"
 
 
 def measured_peak():
@@ -53,6 +58,33 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json (device copy, measured)"
     except Exception:
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def bind_to_gpu_numa_node(index):
+    """Run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off:
+    with 8 ranks on one box, host buffers on the wrong socket cross the inter-socket link on every
+    upload.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa node unknown (single node or virtualised)"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += range(int(lo), int(hi or lo) + 1)
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"bound to numa node {node} ({len(allowed)} cpus)"
+        return f"numa node {node}: no allowed cpus, not bound"
+    except Exception as e:  # best effort: never fail the bench over affinity
+        return f"not bound ({type(e).__name__})"
 
 
 class ClockSampler:
@@ -124,7 +156,9 @@ def make_cloud(rank):
 def run_reference(args):
     """The reference's own CPU implementation of the path (oracle/_ref: src/receiver.cpp +
     include/map2D.h compiled against inert shims), single-threaded like its initial-build
-    loop (the OpenMP pragma at src/receiver.cpp:149 is commented out)."""
+    loop (the OpenMP pragma at src/receiver.cpp:149 is commented out).  `value` counts only the
+    reference's own two stage timers ("division time" + "calculate time", src/receiver.cpp:148-162):
+    the harness's copy into the reference containers and the teardown of its maps are excluded."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -138,25 +172,115 @@ def run_reference(args):
     p = default_params(GRID_LEN, Z_LEN, INTERVAL)
     for _ in range(args.warmup):
         fn(cloud[: REF_STEP_POINTS // 8], p)
-    t0 = time.perf_counter()
+    stage_s, t0 = 0.0, time.perf_counter()
     for _ in range(args.steps):
-        fn(cloud, p)
-    dt = time.perf_counter() - t0
-    value = REF_STEP_POINTS * args.steps / dt
-    sample = f"first {REF_STEP_POINTS} points of the 10M-point cfg2 cloud per step (sweep order), {kind} build"
+        r = fn(cloud, p)
+        stage_s += r.division_s + r.calculate_s
+    wall = time.perf_counter() - t0
+    value = REF_STEP_POINTS * args.steps / stage_s
+    sample = (f"first {REF_STEP_POINTS} points of the 10M-point cfg2 cloud per step (the GPU arm builds all 10M per step), {kind} build; "
+              f"value = points / (division + calculate timers of the reference, {stage_s / args.steps:.2f} s per step); wall incl. harness {wall / args.steps:.2f} s per step")
     line = {
         "impl": "reference", "metric": "ndt_map_build_points_per_sec", "value": value, "unit": "points/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * stage_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 multi-level bridge/underpass scene, 0.2 m cells, z 0.1 m, slope_interval 0.08 (BASELINE configs[1])",
-                   "points_per_step": REF_STEP_POINTS},
+        "config": {"workload": WORKLOAD, "points_per_step": REF_STEP_POINTS,
+                   "subsample": "the CPU arm times a 1M-point prefix of the same cloud per step (10M points take about 20 s per step on one core); points/s is size-normalised"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_points_per_s_incl_harness": REF_STEP_POINTS * args.steps / wall,
         "gpu_launches": 0,
     }
     args.json_out.write(json.dumps(line) + "\n")
     args.json_out.flush()
     return 0
+
+
+def multi_gpu_parity(rank, world, local):
+    """Outside the timed region: one 2 M-point cloud cut into `world` strips, built, exchanged,
+    and (rank 0) compared with the oracle to the full parity bar (tests/parity.py)."""
+    import torch
+    from grid_ndt_b200 import synthetic
+    from grid_ndt_b200._abi import default_params
+    from grid_ndt_b200.tiles import TiledTwoDmap
+    cloud = synthetic.cfg2(2_000_000, scale=0.2 ** 0.5)
+    origin = [float(v) for v in cloud[0, :3]]
+    dev_cloud = torch.from_numpy(cloud).cuda()
+    tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, capacity=3_000_000)
+    cuts = tm.plan(dev_cloud, origin=origin)
+    tm.build(dev_cloud, "slope", origin=origin, cuts=cuts, filter_points=True)
+    out = None
+    if rank == 0:
+        from oracle import oracle as O
+        from tests import parity
+        p = default_params(GRID_LEN, Z_LEN, INTERVAL, origin=origin, origin_is_first_point=0)
+        o32, o64 = O.oracle_build(cloud, p, "faithful32"), O.oracle_build(cloud, p, "truth64")
+        rep = parity.compare_gathered(tm.gathered_numpy("voxels"), tm.gathered_numpy("columns"), tm.gathered_numpy("slopes"), o32, o64, p)
+        unexplained = (rep.get("label_mismatch", 0) - rep.get("label_mismatch_agreeing_with_truth64", 0) - rep.get("label_mismatch_threshold_adjacent", 0)
+                       + rep.get("reach_mismatch", 0) - rep.get("reach_mismatch_agreeing_with_truth64", 0) - rep.get("reach_mismatch_threshold_adjacent", 0))
+        out = {"points": int(cloud.shape[0]), "strips": world, "voxels": int(len(o32.voxels)), "ok": bool(rep["ok"]),
+               "label_mismatch": rep.get("label_mismatch"), "reach_mismatch": rep.get("reach_mismatch"), "unexplained": int(unexplained) if rep["ok"] else -1,
+               "exact_fields": "sx sy sz count first_index column slope: bit-exact" if rep["ok"] else rep["fail"],
+               "mean_max_rel_err": rep.get("mean_max_rel_err"), "scatter_max_rel_err": rep.get("scatter_max_rel_err"), "evals_max_rel_err": rep.get("evals_max_rel_err")}
+    else:
+        tm.synchronize()
+    tm.close()
+    del dev_cloud
+    torch.cuda.empty_cache()
+    return out
+
+
+def target_cfg3(rank, world, local, dev, peak):
+    """North star: ONE cloud (cfg3 terrain, 50 M points, 0.1 m cells) strong-scaled over the N
+    strips, whole map (Slope + Cell tables) gathered on every GPU; cloud resident in HBM."""
+    import torch
+    import torch.distributed as dist
+    from grid_ndt_b200 import synthetic
+    from grid_ndt_b200.tiles import TiledTwoDmap
+    n = TARGET_POINTS
+    cloud = synthetic.cfg3(n, extent=224.0 * (n / 50e6) ** 0.5)  # same seed on every rank
+    origin = [float(v) for v in cloud[0, :3]]
+    full = torch.from_numpy(cloud).cuda()
+    tm = TiledTwoDmap(0.1, 0.1, INTERVAL, rank, world, device=local, halo_records=65536, gather=("slopes", "columns"),
+                      capacity=int(0.2 * n) + 1_000_000)
+    cuts = tm.plan(full, origin=origin)
+    rows = {}
+    for mode in ("full", "share"):
+        if mode == "full":
+            src, filt = full, True
+        else:  # this rank's strip only: the reference's x index (map2D.h:965-970) evaluated on the host
+            d = cloud[:, 0] - np.float32(origin[0])
+            k = np.maximum(np.ceil((np.abs(d) / np.float32(0.1)).astype(np.float32)), 1).astype(np.int64)
+            cx = np.where(cloud[:, 0] > np.float32(origin[0]), k - 1, -k)
+            src, filt = torch.from_numpy(np.ascontiguousarray(cloud[(cx >= cuts[rank]) & (cx < cuts[rank + 1])])).cuda(), False
+        fn = (lambda: tm.build(src, "slope", origin=origin, cuts=cuts, filter_points=filt))
+        for _ in range(2):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 5
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        total_vox = int(tm.offsets[-1])
+        b_alg = 16.0 * n + 96.0 * total_vox
+        rows[mode] = {"ms_per_build": ms, "points_per_s": n / ms * 1e3, "frac_of_aggregate_peak": b_alg / ms / 1e6 / (peak * world),
+                      "voxels": total_vox, "meets_10ms": bool(ms < 10.0)}
+        del src
+    tm.close()
+    del full
+    torch.cuda.empty_cache()
+    rows["what"] = (f"ONE cfg3 terrain cloud, {n // 1_000_000}M points, 0.1 m cells, x strips over {world} GPUs, Slope + Cell tables of the whole map "
+                    "gathered on every GPU through peer-mapped memory; 'full': every GPU holds the whole cloud and filters its strip in the first pass, "
+                    "'share': every GPU holds only its strip's points; target < 10 ms on 8 GPUs at >= 60 % of the aggregate HBM roofline")
+    return rows
 
 
 def main():
@@ -166,6 +290,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the parity and target_cfg3 legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE line, the JSON: everything else any library writes to fd 1
@@ -188,6 +313,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -199,13 +325,15 @@ def main():
 
     if world > 1:
         from grid_ndt_b200.tiles import TiledTwoDmap
+        cap = int(0.08 * n_pts * world) + 1_000_000  # voxels of the whole map (cfg2: 0.055 per point)
+        gather = ("slopes", "columns")              # what the host planner reads (Cell / Slope, map2D.h:136-187)
         # DEPTH builders deep: the NVLink gather of build i overlaps the SM work of the next builds
-        tmp = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=DEPTH)
-        tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=1)  # one at a time (e2e)
+        tmp = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=DEPTH, gather=gather, capacity=cap)
+        tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=1, gather=gather, capacity=cap)  # one at a time
         m = tm.map
 
         def step(src):
-            tm.build(src, "slope", origin=origin, cuts=None, filter_points=False)
+            return tm.build(src, "slope", origin=origin, cuts=None, filter_points=False)
 
         def run_steps(src, k):
             n_launch = 0
@@ -245,6 +373,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
     run_steps(resident, args.warmup)
     step(resident)
     barrier()
@@ -255,12 +390,7 @@ def main():
         launches = run_steps(resident, args.steps)
         ev1.record()
         barrier()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     total_pts = n_pts * world
     value = total_pts / (ms_per_step * 1e-3)
     # one build at a time (latency of a single cloud), same events, outside the headline region
@@ -272,36 +402,55 @@ def main():
         step(resident)
     es1.record()
     barrier()
-    serial_ms = es0.elapsed_time(es1) / n_serial
+    serial_ms = max_over_ranks(es0.elapsed_time(es1)) / n_serial
+    # stage split of one build alone (stage events cost a little: kept out of the numbers above)
+    m.stage_timing(True)
+    step(resident)
+    barrier()
     counts = m.counts()
     stages = m.stage_ms()
+    layout = m.key_layout()
+    m.stage_timing(False)
 
-    # ---- end to end: pinned host cloud in, tables out (into pinned host buffers), every step
+    # ---- end to end: pinned host cloud in, result tables out (into pinned host buffers), every step
     m.pin_results(True)
+    if world > 1:
+        pin = {}
 
-    def e2e_step():
-        step(host)
-        v, s, c = m.voxels, m.slopes, m.columns
-        return v.nbytes + s.nbytes + c.nbytes
+        def read_back(g):
+            """rank 0: the gathered Slope + Cell tables of the whole map -> pinned host memory."""
+            if rank != 0:
+                return 0
+            total = 0
+            for name, t in (("slopes", g.slopes), ("columns", g.columns)):
+                if name not in pin or pin[name].numel() < t.numel():
+                    pin[name] = torch.empty(int(t.numel() * 1.2) + 4096, dtype=torch.uint8).pin_memory()
+                pin[name][: t.numel()].copy_(t.reshape(-1), non_blocking=True)
+                total += t.numel()
+            torch.cuda.current_stream().synchronize()
+            return total
+
+        def e2e_step():
+            return read_back(step(host))
+    else:
+        def e2e_step():
+            step(host)
+            v, s, c = m.voxels, m.slopes, m.columns
+            return v.nbytes + s.nbytes + c.nbytes
 
     def wall(fn, n):
         barrier()
         t0 = time.perf_counter()
         fn(n)
         barrier()
-        dt = (time.perf_counter() - t0) / n
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
+        return max_over_ranks((time.perf_counter() - t0) / n)
 
     d2h = 0
     for _ in range(2):
         d2h = e2e_step()
     n_e2e = max(3, min(args.steps, 10))
     serial_s = wall(lambda n: [e2e_step() for _ in range(n)], n_e2e)
-    e2e_s, e2e_mode = serial_s, "one build at a time: H2D -> kernels (+ NCCL gather at N>1) -> D2H"
+    e2e_s, e2e_mode = serial_s, "one build at a time: H2D -> kernels (+ peer-memory exchange at N>1) -> D2H"
     if world == 1:
         # the same call, two builders deep: the upload of cloud i+1 overlaps the build and
         # read-back of cloud i (grid_ndt_b200.pipeline.CloudPipeline).  Every step still
@@ -321,31 +470,27 @@ def main():
         e2e_mode = "CloudPipeline depth 2: H2D of cloud i+1 overlaps kernels + D2H of cloud i"
         pipe.close()
     else:
-        # N > 1: the two-deep strip pipeline with HOST input: upload of cloud i+1 overlaps the
-        # gather and the read-back of this rank's strip tables of cloud i
-        for sl in tmp.slots:
-            sl.map.pin_results(True)
-
         def piped(n):
             tmp.submit(host, "slope", origin=origin, cuts=None, filter_points=False)
             for i in range(n):
                 if i + 1 < n:
                     tmp.submit(host, "slope", origin=origin, cuts=None, filter_points=False)
-                tmp.collect()
-                mm = tmp.last_map
-                got = mm.voxels.nbytes + mm.slopes.nbytes + mm.columns.nbytes
-                assert got == d2h, (got, d2h)
+                got = read_back(tmp.collect())
+                assert rank != 0 or got == d2h, (got, d2h)
             tmp.synchronize()
         piped(3)
         e2e_s = wall(piped, n_e2e)
-        e2e_mode = "TiledTwoDmap depth 2, host input: H2D of cloud i+1 overlaps NCCL gather + D2H of cloud i"
+        e2e_mode = (f"TiledTwoDmap depth {tmp.depth}, host input on every rank: H2D of cloud i+1 overlaps the exchange of cloud i; rank 0 reads back "
+                    "the gathered Slope + Cell tables of the whole map (the host planner's input); the other ranks keep theirs on the GPU")
     e2e_value = total_pts / e2e_s
+    d2h = int(max_over_ranks(float(d2h)))
 
     peak, peak_src = measured_peak()
     v_tab = counts["n_voxels"]
     b_alg = 16.0 * n_pts + 96.0 * v_tab            # per GPU per build
-    # device time of the build itself on this rank (stage events; excludes the NCCL gather)
-    t_build_ms = stages["total"]
+    # device time of one build alone: N = 1 the serial loop above (events around back-to-back single builds, no
+    # stage events inside); N > 1 the library's start/end events of this rank's strip build (excludes the exchange)
+    t_build_ms = serial_ms if world == 1 else stages["total"]
     achieved = b_alg / (t_build_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -355,7 +500,6 @@ def main():
         except Exception:
             traffic = None
 
-    layout = m.key_layout()
     n_pass = max(1, layout["passes"])
     pass_ms = stages["sort"] / n_pass
     pass_bytes = 32.0 * n_pts  # every point read once and written once per pass
@@ -368,25 +512,41 @@ def main():
         "metric": "ndt_map_build_points_per_sec", "value": value, "unit": "points/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "ms_per_10M_points": ms_per_step * 1e7 / total_pts, "serial_ms_per_step": serial_ms,
+        "value_latency": total_pts / (serial_ms * 1e-3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2 multi-level bridge/underpass scene, 10M points per GPU, 0.2 m cells, z 0.1 m, slope_interval 0.08, demand slope (BASELINE configs[1])",
+        "config": {"workload": WORKLOAD,
                    "points_per_gpu": n_pts, "voxels_per_gpu": v_tab, "columns_per_gpu": counts["n_columns"], "slopes_per_gpu": counts["n_slopes"],
                    "l2": "inputs (160 MB) and work buffers (320 MB) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": (f"x-strips x{world}: thin halo swap + NCCL gather of finished strips; " if world > 1 else "single GPU; ")
-                                  + (f"{DEPTH if world > 1 else 2} builds in flight on separate streams (serial_ms_per_step = one build at a time)")},
+                   "parallelism": (f"x-strips x{world}: halo rows + gather of the Slope and Cell tables through peer-mapped memory (no NCCL on the data path); "
+                                   if world > 1 else "single GPU; ")
+                                  + (f"{DEPTH if world > 1 else 2} builds in flight on separate streams for `value`; value_latency / serial_ms_per_step = one build at a time"),
+                   "host": numa},
         "stage_ms": stages,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes": b_alg, "kernel_ms": t_build_ms,
                      "dominant_kernel": dominant,
                      "achieved_in_flight": (b_alg / (ms_per_step * 1e-3) / 1e9) if world == 1 else None,
                      "what": "whole build (all kernels of one step) on one GPU, one build at a time: (16 B x points + 96 B x voxels) / "
-                             "device time of the build (stage events); achieved_in_flight = the same bytes / ms_per_step of the timed "
+                             "device time of the build (library start/end events); achieved_in_flight = the same bytes / ms_per_step of the timed "
                              "region (two builds in flight); peak = " + peak_src},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_pts * 16), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_s * 1e3, "mode": e2e_mode, "serial_ms_per_step": serial_s * 1e3},
+                "ms_per_step": e2e_s * 1e3, "mode": e2e_mode, "serial_ms_per_step": serial_s * 1e3,
+                "h2d_gbs_per_gpu_if_copy_bound": n_pts * 16 / e2e_s / 1e9},
         "gpu_launches": launches,
         "clocks": clk.summary(),
     }
+    if world > 1 and not args.no_extras:
+        par = multi_gpu_parity(rank, world, local)
+        bad = torch.tensor([0 if (par is None or (par["ok"] and par["unexplained"] == 0)) else 1], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        line["parity"] = par
+        if int(bad.item()):
+            if rank == 0:
+                sys.stderr.write("multi-GPU parity FAILED: " + json.dumps(par, default=str) + "\n")
+            dist.destroy_process_group()
+            return 1
+        if TARGET_POINTS:
+            line["target_cfg3"] = target_cfg3(rank, world, local, dev, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from grid_ndt_b200._abi import default_params
         from oracle import oracle as O
@@ -396,9 +556,9 @@ def main():
         t0 = time.perf_counter()
         r = fn(sample, default_params(GRID_LEN, Z_LEN, INTERVAL))
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": CPU_BASELINE_POINTS / dt, "unit": "points/s", "cores": 1, "kind": kind,
-                                "sample": f"first {CPU_BASELINE_POINTS} points of the same 10M cloud, one build, {dt:.1f} s "
-                                          f"(division {r.division_s:.1f} s + calculate {r.calculate_s:.1f} s); single thread like the reference's initial-build loop",
+        line["cpu_baseline"] = {"value": CPU_BASELINE_POINTS / (r.division_s + r.calculate_s), "unit": "points/s", "cores": 1, "kind": kind,
+                                "sample": f"first {CPU_BASELINE_POINTS} points of the same 10M cloud, one build: division {r.division_s:.1f} s + calculate {r.calculate_s:.1f} s "
+                                          f"on the reference's own timers ({dt:.1f} s wall incl. the harness); single thread like the reference's initial-build loop",
                                 "host_cores_available": os.cpu_count()}
     if rank == 0:
         args.json_out.write(json.dumps(line) + "\n")

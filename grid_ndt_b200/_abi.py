@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-GNDT_ABI_VERSION = 1
+GNDT_ABI_VERSION = 2
 GNDT_OK, GNDT_ERR_INVALID_ARG, GNDT_ERR_CUDA, GNDT_ERR_CAPACITY, GNDT_ERR_STATE, GNDT_ERR_INTERNAL = 0, -1, -2, -3, -4, -5
 GNDT_MEM_HOST, GNDT_MEM_DEVICE = 0, 1
 GNDT_DEMAND_SLOPE, GNDT_DEMAND_TRUE = 0, 1
@@ -131,3 +131,11 @@ class XchgView(C.Structure):
 
 
 assert C.sizeof(XchgInfo) == 128
+
+
+class PointCloud2(C.Structure):
+    """gndt_pointcloud2 (include/gndt.h): the fields of a sensor_msgs/PointCloud2 the path reads."""
+
+    _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("point_step", C.c_uint32),
+                ("x_offset", C.c_uint32), ("y_offset", C.c_uint32), ("z_offset", C.c_uint32),
+                ("is_bigendian", C.c_uint8), ("host_pinned", C.c_uint8), ("reserved", C.c_uint8 * 2)]

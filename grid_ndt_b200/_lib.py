@@ -5,14 +5,14 @@ import os
 import subprocess
 import sys
 
-from ._abi import Counts, Params, XchgInfo, XchgView
+from ._abi import Counts, Params, PointCloud2, XchgInfo, XchgView
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("GNDT_LIB") or os.path.join(HERE, "libgndt.so")  # GNDT_LIB: tuning variants only
 SOURCES = [os.path.join(HERE, "csrc", f) for f in (
     "gndt_api.cu", "gndt_device.cuh", "gndt_sort.cuh", "gndt_reduce.cuh", "gndt_label.cuh", "gndt_update.cuh",
-    "gndt_exchange.cuh")]
+    "gndt_exchange.cuh", "gndt_graph.cuh")]
 HEADER = os.path.join(REPO, "include", "gndt.h")
 LOOKUP_HEADER = os.path.join(REPO, "include", "gndt_lookup.h")
 
@@ -52,7 +52,10 @@ SYMBOLS = {
     "gndt_destroy": (_i, [_vp]),
     "gndt_set_params": (_i, [_vp, C.POINTER(Params)]),
     "gndt_build": (_i, [_vp, _vp, _sz, _sz, _i, _vp]),
+    "gndt_build_msg": (_i, [_vp, C.POINTER(PointCloud2), _vp]),
     "gndt_update": (_i, [_vp, _vp, _sz, _sz, _i, _vp]),
+    "gndt_remove": (_i, [_vp, _vp, _sz, _sz, _i, _vp]),
+    "gndt_changed_columns": (_i, [_vp, _vp, _sz, _i, C.POINTER(_sz)]),
     "gndt_counts": (_i, [_vp, C.POINTER(Counts)]),
     "gndt_copy_voxels": (_i, [_vp, _vp, _sz, _i, C.POINTER(_sz)]),
     "gndt_copy_slopes": (_i, [_vp, _vp, _sz, _i, C.POINTER(_sz)]),
@@ -63,6 +66,8 @@ SYMBOLS = {
     "gndt_apply_strip_offsets": (_i, [_vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _i, _vp]),
     "gndt_device_count_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "gndt_device_table_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "gndt_build_edges": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "gndt_copy_edges": (_i, [_vp, _vp, _sz, _vp, _sz, _i, C.POINTER(_sz), C.POINTER(_sz)]),
     "gndt_xchg_create": (_i, [_vp, _i, _i, _sz, _sz, _i, C.POINTER(XchgInfo)]),
     "gndt_xchg_connect": (_i, [_vp, C.POINTER(XchgInfo), _i]),
     "gndt_xchg_run": (_i, [_vp, _vp]),

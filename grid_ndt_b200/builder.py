@@ -158,6 +158,30 @@ class TwoDmap:
         self.uniformDivision(cloud)
         return self.create2DMap(demand)
 
+    def chatterCallbackMsg(self, data, width: int, height: int, point_step: int, offsets=(0, 4, 8), is_bigendian: bool = False,
+                           demand: str = "slope", stream: int = 0) -> bool:
+        """chatterCallback straight from a sensor_msgs/PointCloud2 payload (src/receiver.cpp:137-160):
+        `data` = the message's byte buffer (bytes / bytearray / uint8 numpy or torch CPU tensor; a pinned
+        torch tensor is uploaded directly, anything else through the library's pinned ring)."""
+        if demand not in ("slope", "true"):
+            raise GndtError(-1, f"unknown demand {demand!r}")
+        self._p.origin_is_first_point = 1
+        self._p.demand = _abi.GNDT_DEMAND_SLOPE if demand == "slope" else _abi.GNDT_DEMAND_TRUE
+        pinned = False
+        if torch is not None and isinstance(data, torch.Tensor):
+            pinned, ptr, keep = data.is_pinned(), data.data_ptr(), data
+        else:
+            keep = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8)
+            ptr = keep.ctypes.data
+        msg = _abi.PointCloud2(ptr, width, height, point_step, offsets[0], offsets[1], offsets[2], 1 if is_bigendian else 0, 1 if pinned else 0)
+        L = lib()
+        _check(self._h, L.gndt_set_params(self._h, C.byref(self._p)))
+        _check(self._h, L.gndt_build_msg(self._h, C.byref(msg), stream))
+        self._keep = keep
+        self._tables.clear()
+        self._views.clear()
+        return True
+
     def change2DMap(self, scan, stream: Optional[int] = None) -> bool:
         """Fuse one more scan into the resident map (map2D.h:672-822 / receiver.cpp:179-212)."""
         ptr, n, stride, mem, st, keep = self._marshal(scan)
@@ -168,6 +192,33 @@ class TwoDmap:
         self._tables.clear()
         self._views.clear()
         return True
+
+    def del2DMap(self, scan, stream: Optional[int] = None) -> bool:
+        """Take a scan out of the resident map again (map2D.h:826-915 / receiver.cpp:214-248)."""
+        ptr, n, stride, mem, st, keep = self._marshal(scan)
+        if stream is not None:
+            st = stream
+        _check(self._h, lib().gndt_remove(self._h, ptr, n, stride, mem, st))
+        self._keep = keep
+        self._tables.clear()
+        self._views.clear()
+        return True
+
+    @property
+    def changed_columns(self) -> np.ndarray:
+        """Indices (into `columns`) of the cells the last change2DMap / del2DMap touched, in
+        first-touched order: the reference's changeMorton_list (receiver.cpp:47-56)."""
+        n = C.c_size_t()
+        _check(self._h, lib().gndt_changed_columns(self._h, None, 0, _abi.GNDT_MEM_HOST, C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.uint32)
+        _check(self._h, lib().gndt_changed_columns(self._h, out.ctypes.data, len(out), _abi.GNDT_MEM_HOST, C.byref(n)))
+        return out[: n.value]
+
+    @property
+    def changeMorton_list(self):
+        """xy keys of the cells the last scan touched, first-touched order (receiver.cpp:47-56)."""
+        cols = self.columns[self.changed_columns]
+        return list(morton_strings(cols["sx"], cols["sy"]))
 
     # ---- results -------------------------------------------------------------------------
     def counts(self) -> dict:
@@ -217,6 +268,18 @@ class TwoDmap:
         p, n = C.c_void_p(), C.c_size_t()
         _check(self._h, lib().gndt_device_voxels(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def edges(self, slopes_ptr: int = 0, n_slopes: int = 0, columns_ptr: int = 0, n_columns: int = 0):
+        """(offsets[n_slopes + 1], targets) — the traversability graph as CSR: for Slope i the Slopes
+        AccessibleNeighbors (map2D.h:530-548) returns, in the reference's order.  Built on the GPU
+        from this map's tables, or from the device tables given (a gathered multi-GPU map)."""
+        L = lib()
+        _check(self._h, L.gndt_build_edges(self._h, slopes_ptr or None, n_slopes, columns_ptr or None, n_columns, 0))
+        ns, nt = C.c_size_t(), C.c_size_t()
+        _check(self._h, L.gndt_copy_edges(self._h, None, 0, None, 0, _abi.GNDT_MEM_HOST, C.byref(ns), C.byref(nt)))
+        off, tgt = np.zeros(ns.value + 1, np.uint32), np.zeros(max(nt.value, 1), np.uint32)
+        _check(self._h, L.gndt_copy_edges(self._h, off.ctypes.data, len(off), tgt.ctypes.data, len(tgt), _abi.GNDT_MEM_HOST, None, None))
+        return off, tgt[: nt.value]
 
     def plan_tiles(self, cloud, ntiles: int) -> np.ndarray:
         ptr, n, stride, mem, st, keep = self._marshal(cloud)

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 
 #include "gndt_device.cuh"
 #include "gndt_lookup.h"
@@ -19,6 +20,7 @@
 #include "gndt_sort.cuh"
 #include "gndt_update.cuh"
 #include "gndt_exchange.cuh"
+#include "gndt_graph.cuh"
 #include <unistd.h>
 
 using namespace gndt;
@@ -50,8 +52,20 @@ struct gndt_handle {
   Buffer in_stage, buf_a, buf_b, zero;
   // workspace sized by voxels
   Buffer mom, mom_alt, table, slopes, columns, vfirst;
-  // streaming update scratch (sized by the scan)
-  Buffer mom_scan, upd_flags, upd_pos, upd_keys;
+  // PointCloud2 ingest: pinned staging ring for pageable messages, repacked points for odd layouts
+  void *ring = nullptr;
+  cudaEvent_t ring_ev[4] = {};
+  bool ring_used[4] = {};
+  Buffer msg_points;
+  // streaming fusion scratch
+  Buffer mom_scan, upd_work;
+  int pending_fuse = 0;        // +1 / -1: a gndt_update / gndt_remove awaits its verdict (sync_counts)
+  size_t pending_points = 0;
+  Ctl saved_ctl;               // results of the resident map before the pending call
+  gndt_params res_params;      // parameters the resident map was built with
+  const u32 *changed_dev = nullptr, *changed_count_dev = nullptr;
+  size_t n_changed = 0;
+  bool n_changed_valid = false;
   Buffer small;  // Totals + n_new word, never memset by a build
   size_t cap_points = 0, cap_voxels = 0;
   // carved out of `zero`
@@ -73,6 +87,10 @@ struct gndt_handle {
   size_t zero_bytes_used = 0;
   size_t sort_tiles = 0, sort_groups = 0, red_tiles = 0, label_blocks = 0;
   Buffer f_zero;  // scratch of gndt_plan_tiles (x-column histogram)
+  // traversability graph (gndt_build_edges)
+  Buffer g_work, g_off, g_tgt;
+  size_t g_slopes = 0, g_targets = 0;
+  bool g_valid = false;
   // peer-mapped strip exchange (gndt_xchg_*)
   Buffer xbuf;
   XLayout xl = {};
@@ -85,7 +103,7 @@ struct gndt_handle {
   bool built = false;
   bool counts_valid = false;
   Ctl host_ctl;
-  Totals host_tot;
+  Totals host_tot, saved_tot;
   cudaStream_t last_stream = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
   bool timed_h2d = false;
@@ -323,6 +341,31 @@ int sync_counts(gndt_handle *h) {
   GNDT_CUDA(h, cudaMemcpyAsync(&h->host_ctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->last_stream));
   GNDT_CUDA(h, cudaMemcpyAsync(&h->host_tot, h->small.p, sizeof(Totals), cudaMemcpyDeviceToHost, h->last_stream));
   GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  if (h->pending_fuse) {  // verdict of the last gndt_update / gndt_remove
+    const int sign = h->pending_fuse;
+    h->pending_fuse = 0;
+    if (h->host_ctl.err) {
+      // failed on the device: the resident moments were never touched and the tables were not rewritten
+      // (the back end returns at once when the error word is set); put the counters back
+      const u32 e = h->host_ctl.err;
+      h->host_ctl = h->saved_ctl;
+      h->host_tot = h->saved_tot;
+      GNDT_CUDA(h, cudaMemcpyAsync(h->ctl, &h->saved_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, h->last_stream));
+      GNDT_CUDA(h, cudaMemcpyAsync(h->small.p, &h->saved_tot, sizeof(Totals), cudaMemcpyHostToDevice, h->last_stream));
+      GNDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+      h->counts_valid = true;  // the map before the call stays valid
+      if (e & kErrWatchdog) { h->err = "device watchdog tripped (look-back / TMA wait never resolved)"; return GNDT_ERR_INTERNAL; }
+      if (e & kErrUnmatched) { h->err = "gndt_remove: the scan holds points that were never fused into the map; map unchanged"; return GNDT_ERR_STATE; }
+      h->err = "voxel table capacity (max_voxels) exceeded; map unchanged";
+      return GNDT_ERR_CAPACITY;
+    }
+    std::swap(h->mom, h->mom_alt);
+    if (sign > 0) h->total_points += h->pending_points;
+    u32 nc = 0;
+    GNDT_CUDA(h, cudaMemcpy(&nc, h->changed_count_dev, 4, cudaMemcpyDeviceToHost));
+    h->n_changed = nc;
+    h->n_changed_valid = true;
+  }
   if (h->host_ctl.err & kErrWatchdog) { h->err = "device watchdog tripped (look-back / TMA wait never resolved)"; return GNDT_ERR_INTERNAL; }
   if (h->host_ctl.err & kErrCapacity) { h->err = "voxel table capacity (max_voxels) exceeded"; return GNDT_ERR_CAPACITY; }
   h->counts_valid = true;
@@ -406,7 +449,7 @@ int check_cloud_args(gndt_handle *h, const void *xyz, size_t n, size_t stride_by
 
 extern "C" {
 
-const char *gndt_version(void) { return "gndt 0.2 (abi 1, sm_100a)"; }
+const char *gndt_version(void) { return "gndt 0.3 (abi 2, sm_100a)"; }
 
 const char *gndt_last_error(const gndt_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -466,8 +509,9 @@ int gndt_destroy(gndt_handle *h) {
   cudaSetDevice(h->device);
   for (int r = 0; r < kMaxRanks; ++r)
     if (h->x_opened[r]) cudaIpcCloseMemHandle(h->x_opened[r]);
+  if (h->ring) { cudaFreeHost(h->ring); for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]); }
   Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
-                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_flags, &h->upd_pos, &h->upd_keys, &h->small, &h->lookback, &h->f_zero, &h->xbuf};
+                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_work, &h->msg_points, &h->small, &h->lookback, &h->f_zero, &h->xbuf, &h->g_work, &h->g_off, &h->g_tgt};
   for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
   for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -481,6 +525,27 @@ int gndt_set_params(gndt_handle *h, const gndt_params *params) {
   int rc = verify_fast_div(h, h->params.grid_len, h->div[0]);  // no-op when the length is unchanged
   if (rc == GNDT_OK) rc = verify_fast_div(h, h->params.z_len, h->div[1]);
   return rc;
+}
+
+// the build proper, cloud already on the device (reserve() done by the caller)
+static int build_device(gndt_handle *h, const float *d_in, size_t n, size_t stride_bytes, cudaStream_t st) {
+  const size_t start = h->params.origin_is_first_point ? 1 : 0;
+  const DevParams dp = make_dev(h, h->params, h->cap_voxels);
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
+  int rc = front_end(h, st, d_in, n, stride_bytes / 4, start, dp, (VoxMoments *)h->mom.p);
+  if (rc != GNDT_OK) return rc;
+  launch(h, totals_kernel, 1, 32, 0, st, (Totals *)h->small.p, (const Ctl *)h->ctl, (u64)n, 1, 1);
+  rc = back_end(h, st, dp, (const VoxMoments *)h->mom.p, false);
+  if (rc != GNDT_OK) return rc;
+  GNDT_CUDA(h, cudaGetLastError());
+  h->built = true;
+  h->pending_fuse = 0;
+  h->n_changed_valid = false;
+  h->res_params = h->params;
+  h->stages_valid = h->stage_timing;
+  h->total_points = n;
+  h->last_stream = st;
+  return GNDT_OK;
 }
 
 int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
@@ -504,50 +569,141 @@ int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, i
     d_in = static_cast<const float *>(h->in_stage.p);
     h->timed_h2d = true;
   }
-  const size_t start = h->params.origin_is_first_point ? 1 : 0;
-  const DevParams dp = make_dev(h, h->params, h->cap_voxels);
+  return build_device(h, d_in, n, stride_bytes, st);
+}
 
-  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
-  rc = front_end(h, st, d_in, n, stride_bytes / 4, start, dp, (VoxMoments *)h->mom.p);
-  if (rc != GNDT_OK) return rc;
-  launch(h, totals_kernel, 1, 32, 0, st, (Totals *)h->small.p, (const Ctl *)h->ctl, (u64)n, 1);
-  rc = back_end(h, st, dp, (const VoxMoments *)h->mom.p, false);
-  if (rc != GNDT_OK) return rc;
-  GNDT_CUDA(h, cudaGetLastError());
-  h->built = true;
-  h->stages_valid = h->stage_timing;
-  h->total_points = n;
-  h->last_stream = st;
+// ---- sensor_msgs/PointCloud2 ingest ------------------------------------------------------
+// Any field layout -> packed 16-byte (x, y, z, 0) points: byte-wise reads, optional byte swap.
+__global__ void ingest_kernel(const unsigned char *raw, size_t n, u32 point_step, u32 xo, u32 yo, u32 zo, int big_endian, float4 *out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned char *p = raw + i * point_step;
+    u32 w[3];
+    const u32 offs[3] = {xo, yo, zo};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned char *q = p + offs[k];
+      w[k] = big_endian ? ((u32)q[0] << 24 | (u32)q[1] << 16 | (u32)q[2] << 8 | (u32)q[3])
+                        : ((u32)q[3] << 24 | (u32)q[2] << 16 | (u32)q[1] << 8 | (u32)q[0]);
+    }
+    out[i] = make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), 0.f);
+  }
+}
+
+// Pageable host memory -> device through a ring of pinned chunks: the host copy of chunk i + 1
+// (split over a few threads) runs while the DMA engine moves chunk i.  A plain cudaMemcpyAsync
+// from pageable memory is staged by the driver one small buffer at a time and blocks the caller.
+static int upload_pageable(gndt_handle *h, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  constexpr size_t kChunk = 8u << 20;
+  constexpr int kSlots = 4, kThreads = 4;
+  if (!h->ring) {
+    GNDT_CUDA(h, cudaHostAlloc(&h->ring, kChunk * kSlots, cudaHostAllocDefault));
+    for (int i = 0; i < kSlots; ++i) GNDT_CUDA(h, cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+  }
+  size_t off = 0;
+  for (int slot = 0; off < bytes; slot = (slot + 1) % kSlots) {
+    const size_t len = std::min(kChunk, bytes - off);
+    char *stage = static_cast<char *>(h->ring) + (size_t)slot * kChunk;
+    if (h->ring_used[slot]) GNDT_CUDA(h, cudaEventSynchronize(h->ring_ev[slot]));  // its previous DMA is done
+    const char *from = static_cast<const char *>(src) + off;
+    std::thread workers[kThreads - 1];
+    const size_t part = (len + kThreads - 1) / kThreads;
+    for (int t = 1; t < kThreads; ++t)
+      workers[t - 1] = std::thread([=] { if (t * part < len) memcpy(stage + t * part, from + t * part, std::min(part, len - t * part)); });
+    memcpy(stage, from, std::min(part, len));
+    for (auto &w : workers) w.join();
+    GNDT_CUDA(h, cudaMemcpyAsync(static_cast<char *>(dst) + off, stage, len, cudaMemcpyHostToDevice, st));
+    GNDT_CUDA(h, cudaEventRecord(h->ring_ev[slot], st));
+    h->ring_used[slot] = true;
+    off += len;
+  }
   return GNDT_OK;
 }
 
-int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
+int gndt_build_msg(gndt_handle *h, const gndt_pointcloud2 *msg, void *stream) {
+  if (!h || !msg) return GNDT_ERR_INVALID_ARG;
+  const size_t n = (size_t)msg->width * msg->height;
+  const u32 ps = msg->point_step;
+  if (!msg->data || n == 0 || ps < 12 || msg->x_offset + 4 > ps || msg->y_offset + 4 > ps || msg->z_offset + 4 > ps) {
+    h->err = "gndt_build_msg: empty message or x/y/z fields outside point_step";
+    return GNDT_ERR_INVALID_ARG;
+  }
+  if (n > GNDT_MAX_POINTS) { h->err = "gndt_build_msg: width * height exceeds GNDT_MAX_POINTS"; return GNDT_ERR_CAPACITY; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  h->built = false;
+  h->counts_valid = false;
+  h->launches = 0;
+  const size_t cap_vox = h->params.max_voxels ? (size_t)h->params.max_voxels : n;
+  int rc = reserve(h, n, cap_vox, true, ps, 0, st);
+  if (rc != GNDT_OK) return rc;
+  GNDT_CUDA(h, cudaEventRecord(h->ev[EV_H2D0], st));
+  if (msg->host_pinned) GNDT_CUDA(h, cudaMemcpyAsync(h->in_stage.p, msg->data, n * ps, cudaMemcpyHostToDevice, st));
+  else if ((rc = upload_pageable(h, h->in_stage.p, msg->data, n * ps, st)) != GNDT_OK) return rc;
+  h->timed_h2d = true;
+  // little-endian float32 x, y, z side by side on a 4-byte boundary: the kernels read the message as it is
+  const bool direct = !msg->is_bigendian && (ps % 4 == 0) && (msg->x_offset % 4 == 0) && msg->y_offset == msg->x_offset + 4 &&
+                      msg->z_offset == msg->x_offset + 8;
+  if (direct) return build_device(h, reinterpret_cast<const float *>(static_cast<const char *>(h->in_stage.p) + msg->x_offset), n, ps, st);
+  if ((rc = ensure(h, h->msg_points, n * sizeof(float4))) != GNDT_OK) return rc;
+  ingest_kernel<<<grid_for(h, n, 256, 8), 256, 0, st>>>(static_cast<const unsigned char *>(h->in_stage.p), n, ps, msg->x_offset, msg->y_offset,
+                                                        msg->z_offset, msg->is_bigendian ? 1 : 0, static_cast<float4 *>(h->msg_points.p));
+  h->launches += 1;
+  return build_device(h, static_cast<const float *>(h->msg_points.p), n, sizeof(float4), st);
+}
+
+// gndt_update (sign = +1) and gndt_remove (sign = -1): reduce the scan to its own sorted moments
+// table, merge it with the resident one into the alternate buffer, relabel, list the touched cells.
+static int fuse_scan(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream, int sign) {
+  const char *who = sign > 0 ? "gndt_update" : "gndt_remove";
   if (!h) return GNDT_ERR_INVALID_ARG;
-  int rc = check_cloud_args(h, xyz, n, stride_bytes, mem, "gndt_update");
+  int rc = check_cloud_args(h, xyz, n, stride_bytes, mem, who);
   if (rc != GNDT_OK) return rc;
   // like the reference (map2D.h:679-680: change2DMap returns false on an empty map) an
   // update needs a resident map; its origin and parameters are kept
   if ((rc = sync_counts(h)) != GNDT_OK) return rc;
-  if (h->total_points + n > 0xFFFFFFFFull) { h->err = "gndt_update: more than 2^32 points fused"; return GNDT_ERR_CAPACITY; }
+  if (h->params.grid_len != h->res_params.grid_len || h->params.z_len != h->res_params.z_len ||
+      h->params.tile_lo != h->res_params.tile_lo || h->params.tile_hi != h->res_params.tile_hi) {
+    h->err = std::string(who) + ": grid_len / z_len / strip range differ from the resident map's (two key spaces cannot be fused)";
+    return GNDT_ERR_STATE;
+  }
+  if (sign > 0 && h->total_points + n > 0xFFFFFFFFull) { h->err = "gndt_update: more than 2^32 points fused"; return GNDT_ERR_CAPACITY; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GNDT_CUDA(h, cudaSetDevice(h->device));
   const u32 n_res = h->host_ctl.n_voxels;
   const float origin[3] = {h->host_ctl.origin[0], h->host_ctl.origin[1], h->host_ctl.origin[2]};
+  h->saved_ctl = h->host_ctl;  // what sync_counts restores if this call fails on the device
+  h->saved_tot = h->host_tot;
   h->counts_valid = false;
   h->launches = 0;
+  h->n_changed_valid = false;
 
   // capacity: every scan point could open a new voxel
   size_t cap_vox = h->cap_voxels;
-  const size_t need = (size_t)n_res + n;
+  const size_t need = (size_t)n_res + (sign > 0 ? n : 0);
   if (h->params.max_voxels == 0 && need > cap_vox) cap_vox = need + need / 2;
   rc = reserve(h, n > h->cap_points ? n : h->cap_points, cap_vox, mem == GNDT_MEM_HOST, stride_bytes,
                (size_t)n_res * sizeof(VoxMoments), st);
   if (rc != GNDT_OK) return rc;
   if ((rc = ensure(h, h->mom_alt, cap_vox * sizeof(VoxMoments))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->mom_scan, n * sizeof(VoxMoments))) != GNDT_OK) return rc;
-  if ((rc = ensure(h, h->upd_flags, n * sizeof(u32))) != GNDT_OK) return rc;
-  if ((rc = ensure(h, h->upd_pos, n * sizeof(u32))) != GNDT_OK) return rc;
-  if ((rc = ensure(h, h->upd_keys, n * sizeof(u64))) != GNDT_OK) return rc;
+  // scratch: per scan voxel / point (n + 1 words each): is_new, new_pos, order, valid, order_pos, changed; keys (u64)
+  //          per resident / merged voxel (cap_vox + 1 words each): inv, dead, dead_pos, touch_first
+  //          scan state for the largest of the two
+  const size_t wn = align_up((n + 1) * 4, 256), wv = align_up((cap_vox + 1) * 4, 256);
+  const size_t scan_tiles = (std::max(n, cap_vox) + kScanTile - 1) / kScanTile + 1;
+  const size_t w_state = align_up(scan_tiles * sizeof(u64), 256), w_groups = align_up((scan_tiles / kScanGroup + 2) * sizeof(GroupState), 256);
+  const size_t w_scan = 256 + w_state + w_groups;  // ScanCtl | state | groups: one per scan launched (3)
+  if ((rc = ensure(h, h->upd_work, 6 * wn + align_up(n * 8, 256) + 4 * wv + 3 * w_scan)) != GNDT_OK) return rc;
+  char *w = static_cast<char *>(h->upd_work.p);
+  u32 *is_new = (u32 *)w, *new_pos = (u32 *)(w + wn), *order = (u32 *)(w + 2 * wn), *valid = (u32 *)(w + 3 * wn),
+      *order_pos = (u32 *)(w + 4 * wn), *changed = (u32 *)(w + 5 * wn);
+  u64 *new_keys = (u64 *)(w + 6 * wn);
+  char *wv0 = w + 6 * wn + align_up(n * 8, 256);
+  u32 *inv = (u32 *)wv0, *dead = (u32 *)(wv0 + wv), *dead_pos = (u32 *)(wv0 + 2 * wv), *touch_first = (u32 *)(wv0 + 3 * wv);
+  char *ws = wv0 + 4 * wv;
+  auto scan_ctl = [&](int k) { return reinterpret_cast<ScanCtl *>(ws + k * w_scan); };
+  auto scan_state = [&](int k) { return reinterpret_cast<u64 *>(ws + k * w_scan + 256); };
+  auto scan_groups = [&](int k) { return reinterpret_cast<GroupState *>(ws + k * w_scan + 256 + w_state); };
 
   const float *d_in = static_cast<const float *>(xyz);
   h->timed_h2d = false;
@@ -561,30 +717,66 @@ int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, 
   p.origin_is_first_point = 0;
   p.origin[0] = origin[0]; p.origin[1] = origin[1]; p.origin[2] = origin[2];
   DevParams dp = make_dev(h, p, cap_vox);
-  dp.idx_offset = (u32)h->total_points;
+  dp.idx_offset = sign > 0 ? (u32)h->total_points : 0u;
 
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_START], st));
   VoxMoments *res = (VoxMoments *)h->mom.p, *scan = (VoxMoments *)h->mom_scan.p, *merged = (VoxMoments *)h->mom_alt.p;
   rc = front_end(h, st, d_in, n, stride_bytes / 4, 0, dp, scan);
   if (rc != GNDT_OK) return rc;
-  totals_kernel<<<1, 32, 0, st>>>((Totals *)h->small.p, h->ctl, (u64)n, 0);
+  totals_kernel<<<1, 32, 0, st>>>((Totals *)h->small.p, h->ctl, (u64)n, 0, sign);
   u32 *n_new = reinterpret_cast<u32 *>(static_cast<char *>(h->small.p) + 128);
-  const int g_scan = grid_for(h, n, 256, 8), g_res = grid_for(h, n_res, 256, 8);
-  update_match_kernel<<<g_scan, 256, 0, st>>>(h->ctl, res, n_res, scan, (u32 *)h->upd_flags.p);
-  update_compact_kernel<<<1, 1024, 0, st>>>(h->ctl, scan, (const u32 *)h->upd_flags.p, (u32 *)h->upd_pos.p,
-                                            (u64 *)h->upd_keys.p, n_new);
-  update_prepare_backend_kernel<<<1, 32, 0, st>>>(h->ctl, n_res, n_new);
-  update_merge_resident_kernel<<<g_res, 256, 0, st>>>(res, n_res, (const u64 *)h->upd_keys.p, n_new, merged);
-  update_merge_new_kernel<<<g_scan, 256, 0, st>>>(h->ctl, res, n_res, scan, (const u32 *)h->upd_flags.p,
-                                                  (const u32 *)h->upd_pos.p, n_new, merged, (u32)cap_vox);
-  h->launches += 6;
+  const int g_scan = grid_for(h, n, 256, 8), g_res = grid_for(h, std::max<size_t>(n_res, 1), 256, 8);
+  // zero: is_new .. valid (4 arrays), dead / dead_pos, scan states; 0xFF: inv, touch_first
+  GNDT_CUDA(h, cudaMemsetAsync(is_new, 0, 4 * wn, st));
+  GNDT_CUDA(h, cudaMemsetAsync(dead, 0, 2 * wv, st));
+  GNDT_CUDA(h, cudaMemsetAsync(ws, 0, 3 * w_scan, st));
+  GNDT_CUDA(h, cudaMemsetAsync(inv, 0xFF, wv, st));
+  GNDT_CUDA(h, cudaMemsetAsync(touch_first, 0xFF, wv, st));
+  update_match_kernel<<<g_scan, 256, 0, st>>>(h->ctl, res, n_res, scan, sign, inv, is_new, dead);
+  const int g_tiles_n = grid_for(h, (n + kScanTile - 1) / kScanTile, 1, 4), g_tiles_v = grid_for(h, ((size_t)n_res + kScanTile - 1) / kScanTile, 1, 4);
+  exclusive_scan_kernel<<<g_tiles_n, 256, 0, st>>>(scan_ctl(0), is_new, 0u, &h->ctl->n_voxels, new_pos, scan_state(0), scan_groups(0));
+  if (sign < 0) exclusive_scan_kernel<<<g_tiles_v, 256, 0, st>>>(scan_ctl(1), dead, n_res, nullptr, dead_pos, scan_state(1), scan_groups(1));
+  update_new_keys_kernel<<<g_scan, 256, 0, st>>>(h->ctl, scan, is_new, new_pos, new_keys);
+  update_prepare_kernel<<<1, 32, 0, st>>>(h->ctl, n_res, new_pos, sign < 0 ? dead_pos : nullptr, (u32)cap_vox, n_new);
+  update_merge_resident_kernel<<<g_res, 256, 0, st>>>(h->ctl, res, n_res, scan, sign, inv, new_keys, n_new, dead, dead_pos, merged);
+  if (sign > 0) update_merge_new_kernel<<<g_scan, 256, 0, st>>>(h->ctl, res, n_res, scan, is_new, new_pos, merged);
+  h->launches += 6 + (sign < 0 ? 1 : 1);
   rc = back_end(h, st, dp, merged, true);
   if (rc != GNDT_OK) return rc;
+  // the cells this scan touched, in first-touched order (changeMorton_list)
+  changed_mark_kernel<<<g_scan, 256, 0, st>>>(h->ctl, scan, (const gndt_column *)h->columns.p, touch_first);
+  changed_order_kernel<<<grid_for(h, cap_vox, 256, 8), 256, 0, st>>>(h->ctl, touch_first, dp.idx_offset, (u32)n, order, valid);
+  exclusive_scan_kernel<<<g_tiles_n, 256, 0, st>>>(scan_ctl(2), valid, (u32)n, nullptr, order_pos, scan_state(2), scan_groups(2));
+  changed_compact_kernel<<<g_scan, 256, 0, st>>>(order, valid, order_pos, (u32)n, changed);
+  h->launches += 4;
   GNDT_CUDA(h, cudaGetLastError());
-  std::swap(h->mom, h->mom_alt);
+  h->changed_dev = changed;
+  h->changed_count_dev = &scan_ctl(2)->total;
+  h->pending_fuse = sign;         // resolved by the next sync_counts: swap the moment tables, or roll back
+  h->pending_points = n;
   h->stages_valid = h->stage_timing;
-  h->total_points += n;
   h->last_stream = st;
+  return GNDT_OK;
+}
+
+int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
+  return fuse_scan(h, xyz, n, stride_bytes, mem, stream, +1);
+}
+
+int gndt_remove(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem, void *stream) {
+  return fuse_scan(h, xyz, n, stride_bytes, mem, stream, -1);
+}
+
+int gndt_changed_columns(gndt_handle *h, uint32_t *idx, size_t cap, int dst_mem, size_t *n_out) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  int rc = sync_counts(h);
+  if (rc != GNDT_OK) return rc;
+  if (!h->n_changed_valid) { h->err = "gndt_changed_columns: the last call on this handle was not a gndt_update / gndt_remove"; return GNDT_ERR_STATE; }
+  if (n_out) *n_out = h->n_changed;
+  if (!idx) return GNDT_OK;  // size query
+  if (h->n_changed > cap) { h->err = "destination capacity too small"; return GNDT_ERR_CAPACITY; }
+  if (h->n_changed)
+    GNDT_CUDA(h, cudaMemcpy(idx, h->changed_dev, h->n_changed * 4, dst_mem == GNDT_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
   return GNDT_OK;
 }
 
@@ -701,6 +893,92 @@ int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capac
   return GNDT_OK;
 }
 
+// ---- traversability graph (CSR of AccessibleNeighbors) -----------------------------------
+int gndt_build_edges(gndt_handle *h, const gndt_slope *slopes, size_t n_slopes, const gndt_column *columns, size_t n_columns,
+                     void *stream) {
+  if (!h || ((slopes == nullptr) != (columns == nullptr))) return GNDT_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  h->g_valid = false;
+  int cx_lo = 0, cx_hi = 0, rc;
+  if (!slopes) {  // this handle's own tables
+    if ((rc = sync_counts(h)) != GNDT_OK) return rc;
+    slopes = static_cast<const gndt_slope *>(h->slopes.p);
+    columns = static_cast<const gndt_column *>(h->columns.p);
+    n_slopes = h->host_ctl.n_slopes;
+    n_columns = h->host_ctl.n_columns;
+    if (!st) st = h->last_stream;
+  }
+  if (n_slopes > 0xFFFFFFFEull || n_columns > 0xFFFFFFFEull) return GNDT_ERR_CAPACITY;
+  if (n_columns) {  // x range of the (sorted) column table
+    gndt_column ends[2];
+    GNDT_CUDA(h, cudaMemcpyAsync(&ends[0], columns, sizeof(gndt_column), cudaMemcpyDeviceToHost, st));
+    GNDT_CUDA(h, cudaMemcpyAsync(&ends[1], columns + n_columns - 1, sizeof(gndt_column), cudaMemcpyDeviceToHost, st));
+    GNDT_CUDA(h, cudaStreamSynchronize(st));
+    cx_lo = ends[0].sx > 0 ? ends[0].sx - 1 : ends[0].sx;
+    cx_hi = ends[1].sx > 0 ? ends[1].sx - 1 : ends[1].sx;
+  }
+  const int n_rows = cx_hi - cx_lo + 1;
+  const u32 S = (u32)n_slopes, C = (u32)n_columns;
+  const size_t n_tiles = (n_slopes + kScanTile - 1) / kScanTile;
+  // work buffer: ctl | rows start/end | scan state | scan groups | slope_col | deg
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_ctl = carve(sizeof(ScanCtl)), o_rs = carve((size_t)n_rows * 4), o_re = carve((size_t)n_rows * 4),
+               o_st = carve((n_tiles + 1) * sizeof(u64)), o_gr = carve((n_tiles / kScanGroup + 1) * sizeof(GroupState));
+  const size_t zero_bytes = off;
+  const size_t o_sc = carve((n_slopes + 1) * 4), o_dg = carve((n_slopes + 1) * 4);
+  if ((rc = ensure(h, h->g_work, off)) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->g_off, (n_slopes + 1) * 4)) != GNDT_OK) return rc;
+  char *w = static_cast<char *>(h->g_work.p);
+  ScanCtl *g = reinterpret_cast<ScanCtl *>(w + o_ctl);
+  u32 *rs = reinterpret_cast<u32 *>(w + o_rs), *re = reinterpret_cast<u32 *>(w + o_re);
+  u32 *slope_col = reinterpret_cast<u32 *>(w + o_sc), *deg = reinterpret_cast<u32 *>(w + o_dg);
+  GNDT_CUDA(h, cudaMemsetAsync(w, 0, zero_bytes, st));
+  GNDT_CUDA(h, cudaMemsetAsync(h->g_off.p, 0, (n_slopes + 1) * 4, st));
+  h->g_slopes = n_slopes;
+  h->g_targets = 0;
+  if (S && C) {
+    const DevParams dp = make_dev(h, h->params, 0);
+    const int grid_c = grid_for(h, C, 256, 8), grid_s = grid_for(h, S, 256, 8);
+    graph_prepare_kernel<<<grid_c, 256, 0, st>>>(columns, C, cx_lo, slope_col, rs, re);
+    graph_edges_kernel<false><<<grid_s, 256, 0, st>>>(slopes, S, columns, C, slope_col, rs, re, cx_lo, n_rows, deg, nullptr, nullptr, dp);
+    exclusive_scan_kernel<<<grid_for(h, n_tiles, 1, 4), 256, 0, st>>>(g, deg, S, nullptr, (u32 *)h->g_off.p,
+                                                                      reinterpret_cast<u64 *>(w + o_st), reinterpret_cast<GroupState *>(w + o_gr));
+    ScanCtl hg;
+    GNDT_CUDA(h, cudaMemcpyAsync(&hg, g, sizeof(hg), cudaMemcpyDeviceToHost, st));
+    GNDT_CUDA(h, cudaStreamSynchronize(st));
+    if (hg.err) { h->err = "graph scan watchdog"; return GNDT_ERR_INTERNAL; }
+    h->g_targets = hg.total;
+    if ((rc = ensure(h, h->g_tgt, std::max<size_t>(hg.total, 1) * 4)) != GNDT_OK) return rc;
+    graph_edges_kernel<true><<<grid_s, 256, 0, st>>>(slopes, S, columns, C, slope_col, rs, re, cx_lo, n_rows, nullptr,
+                                                     (const u32 *)h->g_off.p, (u32 *)h->g_tgt.p, dp);
+    h->launches += 4;
+    GNDT_CUDA(h, cudaStreamSynchronize(st));
+  }
+  GNDT_CUDA(h, cudaGetLastError());
+  h->g_valid = true;
+  return GNDT_OK;
+}
+
+int gndt_copy_edges(gndt_handle *h, uint32_t *offsets, size_t cap_offsets, uint32_t *targets, size_t cap_targets, int dst_mem,
+                    size_t *n_slopes, size_t *n_targets) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  if (!h->g_valid) { h->err = "gndt_copy_edges: call gndt_build_edges first"; return GNDT_ERR_STATE; }
+  if (n_slopes) *n_slopes = h->g_slopes;
+  if (n_targets) *n_targets = h->g_targets;
+  if (!offsets && !targets) return GNDT_OK;  // size query
+  if (cap_offsets < h->g_slopes + 1 || cap_targets < h->g_targets || !offsets || (!targets && h->g_targets)) {
+    h->err = "destination capacity too small";
+    return GNDT_ERR_CAPACITY;
+  }
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  const cudaMemcpyKind kind = dst_mem == GNDT_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  GNDT_CUDA(h, cudaMemcpy(offsets, h->g_off.p, (h->g_slopes + 1) * 4, kind));
+  if (h->g_targets) GNDT_CUDA(h, cudaMemcpy(targets, h->g_tgt.p, h->g_targets * 4, kind));
+  return GNDT_OK;
+}
+
 // ---- peer-mapped strip exchange --------------------------------------------------------
 static_assert(sizeof(gndt_xchg_info) == 128, "gndt_xchg_info is 128 bytes");
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
@@ -806,7 +1084,8 @@ int gndt_xchg_run(gndt_handle *h, void *stream) {
   xchg_halo_edges_kernel<<<grid_for(h, h->cap_voxels, 256, 4), 256, 0, st>>>(
       h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p, reinterpret_cast<const gndt_voxel *>(mine + L.halo[0]),
       reinterpret_cast<const gndt_voxel *>(mine + L.halo[1]), have, dp);
-  xchg_push_kernel<<<h->sm_count, 512, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_slope *)h->slopes.p,
+  static const int push_ctas = [] { const char *e = getenv("GNDT_XCHG_CTAS"); return e ? std::max(1, atoi(e)) : 0; }();
+  xchg_push_kernel<<<push_ctas ? push_ctas : 48, 512, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_slope *)h->slopes.p,
                                                 (const gndt_column *)h->columns.p, X, L, h->x_what, epoch, done_counter);
   xchg_wait_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch);
   h->launches += 6;
@@ -829,14 +1108,16 @@ int gndt_xchg_view_get(gndt_handle *h, gndt_xchg_view *out) {
   out->slopes = (h->x_what & GNDT_X_SLOPES) ? reinterpret_cast<const gndt_slope *>(mine + h->xl.slopes) : nullptr;
   out->columns = (h->x_what & GNDT_X_COLUMNS) ? reinterpret_cast<const gndt_column *>(mine + h->xl.columns) : nullptr;
   out->world = h->xp.world;
+  const int par = h->x_epoch & 1;
   for (int r = 0; r < h->xp.world; ++r) {
-    if (mail.counts[r][3] != h->x_epoch || mail.done[r] != h->x_epoch) { h->err = "exchange incomplete (epoch mismatch)"; return GNDT_ERR_INTERNAL; }
-    out->strip_voxels[r] = mail.counts[r][0];
-    out->strip_columns[r] = mail.counts[r][1];
-    out->strip_slopes[r] = mail.counts[r][2];
-    out->n_voxels += mail.counts[r][0];
-    out->n_columns += mail.counts[r][1];
-    out->n_slopes += mail.counts[r][2];
+    const u32 *c = mail.counts[par][r];
+    if (c[3] != h->x_epoch || mail.done[par][r] != h->x_epoch) { h->err = "exchange incomplete (epoch mismatch)"; return GNDT_ERR_INTERNAL; }
+    out->strip_voxels[r] = c[0];
+    out->strip_columns[r] = c[1];
+    out->strip_slopes[r] = c[2];
+    out->n_voxels += c[0];
+    out->n_columns += c[1];
+    out->n_slopes += c[2];
   }
   return GNDT_OK;
 }

@@ -30,11 +30,14 @@ namespace gndt {
 constexpr int kMaxRanks = 16;
 constexpr u32 kXWaitLimitNs = 4000000000u;  // a peer that never shows up trips the watchdog after 4 s
 
-struct XMail {                 // written by peers (system scope), read by the owner
-  u32 counts[kMaxRanks][4];    // {n_voxels, n_columns, n_slopes, epoch} of every strip
-  u32 halo_epoch[2];           // [0] row from the lower neighbour arrived, [1] from the upper
-  u32 done[kMaxRanks];         // strip r has been pushed into this rank's gathered tables
-  u32 pad[14];
+// Written by peers (system scope), read by the owner.  Two copies of everything, selected by
+// the parity of the epoch: a peer may already be one build ahead on this buffer (it publishes the
+// counts of epoch e + 1 as soon as ITS build is done) while the owner's host still reads epoch e;
+// it cannot be two ahead, because epoch e + 1 completes only after the owner has joined it.
+struct XMail {
+  u32 counts[2][kMaxRanks][4];  // {n_voxels, n_columns, n_slopes, epoch} of every strip
+  u32 halo_epoch[2][2];         // [.][0] row from the lower neighbour arrived, [.][1] from the upper
+  u32 done[2][kMaxRanks];       // strip r has been pushed into this rank's gathered tables
 };
 
 struct XLayout {               // byte offsets inside an exchange buffer (identical on all ranks)
@@ -75,7 +78,7 @@ __global__ void xchg_publish_kernel(const Ctl *ctl, XPeers X, XLayout L, u32 epo
   if (r >= X.world) return;
   const bool bad = ctl->err != 0;
   XMail *m = reinterpret_cast<XMail *>(X.buf[r] + L.mail);
-  u32 *c = m->counts[X.rank];
+  u32 *c = m->counts[epoch & 1][X.rank];
   st_sys(c + 0, bad ? 0u : ctl->n_voxels);
   st_sys(c + 1, bad ? 0u : ctl->n_columns);
   st_sys(c + 2, bad ? 0u : ctl->n_slopes);
@@ -86,13 +89,13 @@ __global__ void xchg_publish_kernel(const Ctl *ctl, XPeers X, XLayout L, u32 epo
 // All strips' counts of this epoch have arrived in the own mailbox (called by one thread).
 __device__ __forceinline__ bool wait_counts(const XMail *mine, int world, u32 epoch) {
   bool ok = true;
-  for (int r = 0; r < world; ++r) ok &= wait_word(&mine->counts[r][3], epoch);
+  for (int r = 0; r < world; ++r) ok &= wait_word(&mine->counts[epoch & 1][r][3], epoch);
   __threadfence_system();
   return ok;
 }
-__device__ __forceinline__ int nearest_nonempty(const XMail *mine, int rank, int world, int dir) {
+__device__ __forceinline__ int nearest_nonempty(const XMail *mine, u32 epoch, int rank, int world, int dir) {
   for (int r = rank + dir; r >= 0 && r < world; r += dir)
-    if (ld_sys(&mine->counts[r][0]) != 0) return r;
+    if (ld_sys(&mine->counts[epoch & 1][r][0]) != 0) return r;
   return -1;
 }
 
@@ -107,7 +110,7 @@ xchg_halo_send_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_column *colu
   if (threadIdx.x == 0) {
     int t = -1;
     if (!wait_counts(mine, X.world, epoch)) atomicOr(&ctl->err, kErrWatchdog);
-    else if (ld_sys(&mine->counts[X.rank][0]) != 0) t = nearest_nonempty(mine, X.rank, X.world, last ? +1 : -1);
+    else if (ld_sys(&mine->counts[epoch & 1][X.rank][0]) != 0) t = nearest_nonempty(mine, epoch, X.rank, X.world, last ? +1 : -1);
     s_target = t;
   }
   __syncthreads();
@@ -145,7 +148,7 @@ xchg_halo_send_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_column *colu
   __syncthreads();
   if (threadIdx.x == 0) {
     XMail *tm = reinterpret_cast<XMail *>(X.buf[target] + L.mail);
-    st_sys(&tm->halo_epoch[slot], epoch);
+    st_sys(&tm->halo_epoch[epoch & 1][slot], epoch);
   }
 }
 
@@ -155,11 +158,11 @@ __global__ void xchg_halo_wait_kernel(Ctl *ctl, XPeers X, XLayout L, u32 epoch, 
   if (threadIdx.x || blockIdx.x) return;
   const XMail *mine = reinterpret_cast<const XMail *>(X.buf[X.rank] + L.mail);
   bool ok = wait_counts(mine, X.world, epoch);
-  const bool self = ld_sys(&mine->counts[X.rank][0]) != 0;
-  const int prev = self ? nearest_nonempty(mine, X.rank, X.world, -1) : -1;
-  const int next = self ? nearest_nonempty(mine, X.rank, X.world, +1) : -1;
-  if (prev >= 0) ok &= wait_word(&mine->halo_epoch[0], epoch);
-  if (next >= 0) ok &= wait_word(&mine->halo_epoch[1], epoch);
+  const bool self = ld_sys(&mine->counts[epoch & 1][X.rank][0]) != 0;
+  const int prev = self ? nearest_nonempty(mine, epoch, X.rank, X.world, -1) : -1;
+  const int next = self ? nearest_nonempty(mine, epoch, X.rank, X.world, +1) : -1;
+  if (prev >= 0) ok &= wait_word(&mine->halo_epoch[epoch & 1][0], epoch);
+  if (next >= 0) ok &= wait_word(&mine->halo_epoch[epoch & 1][1], epoch);
   if (!ok) atomicOr(&ctl->err, kErrWatchdog);
   have[0] = prev >= 0 ? 1 : 0;
   have[1] = next >= 0 ? 1 : 0;
@@ -193,11 +196,40 @@ xchg_halo_edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gn
   }
 }
 
-// X4: push this strip into every rank's gathered tables.  16-byte chunks; the chunk of a record
-// that holds strip-local indices is rewritten with the strip's global offsets on the way.
+// X4: push this strip into every rank's gathered tables.  16-byte chunks, each loaded ONCE and
+// stored to all `world` destinations; the chunk of a record that holds strip-local indices is
+// rewritten with the strip's global offsets on the way.
 //   voxel  (6 chunks): chunk 5 = {rough, flags, column, slope}
 //   slope  (3 chunks): chunk 2 = {normal.z, rough, flags, voxel}
 //   column (2 chunks): chunk 0 = {sx, sy, first_index, voxel_begin}, chunk 1 = {voxel_count, slope_begin, slope_count, reserved}
+// The kernel is NVLink-bound, not SM-bound: a small grid with several loads in flight per thread
+// leaves the SMs to the next build running beside it.
+template <int KIND>  // 0 voxels, 1 slopes, 2 columns
+__device__ __forceinline__ void push_table(const uint4 *src, size_t n_chunks, size_t dst_off_bytes, size_t first_chunk, const XPeers &X,
+                                           const u32 off[3]) {
+  constexpr int kU = 4;
+  constexpr u32 kPer = KIND == 0 ? 6u : (KIND == 1 ? 3u : 2u);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_chunks; i0 += kU * stride) {
+    uint4 v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < n_chunks) v[u] = src[i];
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i >= n_chunks) break;
+      const u32 part = (u32)(i % kPer);
+      if (KIND == 0) { if (part == 5) { v[u].z += off[1]; if (v[u].w != 0xFFFFFFFFu) v[u].w += off[2]; } }
+      else if (KIND == 1) { if (part == 2) v[u].w += off[0]; }
+      else { if (part == 0) v[u].w += off[0]; else v[u].y += off[2]; }
+      for (int p = 0; p < X.world; ++p) reinterpret_cast<uint4 *>(X.buf[p] + dst_off_bytes)[first_chunk + i] = v[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(512)
 xchg_push_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_slope *slopes, const gndt_column *columns, XPeers X, XLayout L,
                  int what, u32 epoch, u32 *done_counter) {
@@ -205,40 +237,18 @@ xchg_push_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_slope *slopes, co
   u32 off[3] = {0, 0, 0}, total[3] = {0, 0, 0};
   for (int r = 0; r < X.world; ++r)
     for (int k = 0; k < 3; ++k) {
-      const u32 c = ld_sys(&mine->counts[r][k]);  // complete: the halo gate ran before in this stream
+      const u32 c = ld_sys(&mine->counts[epoch & 1][r][k]);  // complete: the halo gate ran before in this stream
       if (r < X.rank) off[k] += c;
       total[k] += c;
     }
-  const u32 nv = ld_sys(&mine->counts[X.rank][0]), nc = ld_sys(&mine->counts[X.rank][1]), ns = ld_sys(&mine->counts[X.rank][2]);
+  const u32 *own = mine->counts[epoch & 1][X.rank];
+  const u32 nv = ld_sys(own + 0), nc = ld_sys(own + 1), ns = ld_sys(own + 2);
   const bool fits = total[0] <= L.cap_records;
   if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->err, kErrCapacity);
   if (fits) {
-    const size_t n_vox_chunks = (what & 1) ? (size_t)nv * 6 : 0, n_slope_chunks = (what & 2) ? (size_t)ns * 3 : 0,
-                 n_col_chunks = (what & 4) ? (size_t)nc * 2 : 0;
-    const size_t per_peer = n_vox_chunks + n_slope_chunks + n_col_chunks;
-    const size_t work = per_peer * (size_t)X.world;
-    const uint4 *tv = reinterpret_cast<const uint4 *>(table), *ts = reinterpret_cast<const uint4 *>(slopes),
-                *tc = reinterpret_cast<const uint4 *>(columns);
-    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < work; w += (size_t)gridDim.x * blockDim.x) {
-      // consecutive threads take consecutive chunks of one destination: coalesced on both sides
-      const int p = (int)(w / per_peer);
-      size_t i = w - (size_t)p * per_peer;
-      unsigned char *base = X.buf[p];
-      if (i < n_vox_chunks) {
-        uint4 v = tv[i];
-        if (i % 6 == 5) { v.z += off[1]; if (v.w != 0xFFFFFFFFu) v.w += off[2]; }
-        reinterpret_cast<uint4 *>(base + L.voxels)[(size_t)off[0] * 6 + i] = v;
-      } else if ((i -= n_vox_chunks) < n_slope_chunks) {
-        uint4 v = ts[i];
-        if (i % 3 == 2) v.w += off[0];
-        reinterpret_cast<uint4 *>(base + L.slopes)[(size_t)off[2] * 3 + i] = v;
-      } else {
-        i -= n_slope_chunks;
-        uint4 v = tc[i];
-        if (i % 2 == 0) v.w += off[0]; else v.y += off[2];
-        reinterpret_cast<uint4 *>(base + L.columns)[(size_t)off[1] * 2 + i] = v;
-      }
-    }
+    if (what & 1) push_table<0>(reinterpret_cast<const uint4 *>(table), (size_t)nv * 6, L.voxels, (size_t)off[0] * 6, X, off);
+    if (what & 2) push_table<1>(reinterpret_cast<const uint4 *>(slopes), (size_t)ns * 3, L.slopes, (size_t)off[2] * 3, X, off);
+    if (what & 4) push_table<2>(reinterpret_cast<const uint4 *>(columns), (size_t)nc * 2, L.columns, (size_t)off[1] * 2, X, off);
   }
   // completion: the last CTA to finish raises this strip's `done` flag in every mailbox
   __threadfence_system();
@@ -248,7 +258,7 @@ xchg_push_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_slope *slopes, co
     if (ticket == gridDim.x - 1) {
       *done_counter = 0;
       __threadfence_system();
-      for (int p = 0; p < X.world; ++p) st_sys(&reinterpret_cast<XMail *>(X.buf[p] + L.mail)->done[X.rank], epoch);
+      for (int p = 0; p < X.world; ++p) st_sys(&reinterpret_cast<XMail *>(X.buf[p] + L.mail)->done[epoch & 1][X.rank], epoch);
     }
   }
 }
@@ -258,7 +268,7 @@ __global__ void xchg_wait_kernel(Ctl *ctl, XPeers X, XLayout L, u32 epoch) {
   const int r = threadIdx.x;
   if (r >= X.world) return;
   const XMail *mine = reinterpret_cast<const XMail *>(X.buf[X.rank] + L.mail);
-  if (!wait_word(&mine->done[r], epoch)) atomicOr(&ctl->err, kErrWatchdog);
+  if (!wait_word(&mine->done[epoch & 1][r], epoch)) atomicOr(&ctl->err, kErrWatchdog);
   __threadfence_system();
 }
 

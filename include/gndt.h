@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GNDT_ABI_VERSION 1
+#define GNDT_ABI_VERSION 2
 
 typedef enum gndt_status {
   GNDT_OK = 0,
@@ -186,6 +186,28 @@ int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, i
                void *stream);
 
 /*
+ * The same build straight from a sensor_msgs/PointCloud2 message — what the receiver holds
+ * when its callback fires (src/receiver.cpp:137-143: pcl_conversions::toPCL +
+ * pcl::fromPCLPointCloud2 copy the message twice on the host before the division loop;
+ * src/publisher.cpp:55 is where pcl::toROSMsg wrote it).  Fill the struct from the message:
+ * data = msg.data.data(), width/height/point_step/is_bigendian as they are, *_offset = the
+ * `offset` of the fields named "x", "y", "z" (datatype FLOAT32).  The usual layout
+ * (little-endian, x y z side by side) is read in place on the device; any other layout is
+ * repacked by one small kernel.  host_pinned = 0 (a std::vector<uint8_t> is pageable): the
+ * upload runs through an internal ring of pinned chunks, the host copy of one chunk
+ * overlapping the DMA of the previous one.
+ */
+typedef struct gndt_pointcloud2 {
+  const void *data;
+  uint32_t width, height, point_step;
+  uint32_t x_offset, y_offset, z_offset;
+  uint8_t is_bigendian;
+  uint8_t host_pinned;   /* 1: data is page-locked (cudaHostAlloc / cudaHostRegister) */
+  uint8_t reserved[2];
+} gndt_pointcloud2;
+int gndt_build_msg(gndt_handle *h, const gndt_pointcloud2 *msg, void *stream);
+
+/*
  * Fuse one more scan into the resident map (origin and parameters of the
  * initial build are kept; every point of the scan is binned).
  * Replaces: changeCallback + change2DMap (src/receiver.cpp:179-212;
@@ -195,6 +217,29 @@ int gndt_build(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, i
  */
 int gndt_update(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem,
                 void *stream);
+
+/*
+ * Take a scan out of the resident map again: the inverse of gndt_update (Chan's update run
+ * backwards on the binary64 moments; voxels that lose all their points disappear).
+ * Replaces: delCallback + uniformDelDivision + del2DMap (src/receiver.cpp:95-134,214-248;
+ * include/map2D.h:826-915), commented out at every call site in the reference.  Contract:
+ * build(A) + update(B) + remove(B) equals build(A) (first_index of a surviving voxel keeps
+ * the value it had, which is the same thing whenever B was fused after A).  Every point of
+ * the scan must have been fused before: otherwise the call fails with GNDT_ERR_STATE at the
+ * next result query and the map is left unchanged.
+ */
+int gndt_remove(gndt_handle *h, const void *xyz, size_t n, size_t stride_bytes, int mem,
+                void *stream);
+
+/*
+ * The cells the last gndt_update / gndt_remove touched: indices into the (new) column table,
+ * in the order in which the scan's points first touched them.
+ * Replaces: changeMorton_list (src/receiver.cpp:47-56,187,196; include/map2D.h:505,674-676),
+ * which the reference republishes alone (showInital(change_pub, ..., 1), receiver.cpp:203-206).
+ * idx == NULL: size query.  A failed update / remove (GNDT_ERR_CAPACITY, GNDT_ERR_STATE) leaves
+ * the resident map exactly as it was before the call.
+ */
+int gndt_changed_columns(gndt_handle *h, uint32_t *idx, size_t cap, int dst_mem, size_t *n_out);
 
 /* counters the reference prints (receiver.cpp:144,158; map2D.h:1226) and friends */
 int gndt_counts(gndt_handle *h, gndt_counts_t *out);
@@ -231,6 +276,23 @@ int gndt_apply_strip_offsets(gndt_handle *h, gndt_voxel *table, const uint64_t *
  * count of the last build, and of the table with its capacity in records. */
 int gndt_device_count_ptr(gndt_handle *h, const uint32_t **d_n_voxels); /* -> {n_voxels, n_columns, n_slopes, n_fitted} */
 int gndt_device_table_ptr(gndt_handle *h, const gndt_voxel **dptr, size_t *capacity);
+
+/*
+ * The traversability graph as CSR: for Slope i, targets[offsets[i] .. offsets[i+1]) are the
+ * indices (into the slope table) of the Slopes TwoDmap::AccessibleNeighbors returns for it
+ * (include/map2D.h:530-548: countLRFB :197-263 + countReachable :266-296 + countAngle
+ * :477-482), in the reference's order: left, right, forward, back cell, ascending z inside a
+ * cell.  The GNDT_F_REACH_* bits only say that such a Slope exists; the cost-map expansion
+ * (computeCost, :1285-1397) and A* (GlobalPlan.h:79-83) need the list, several layers per
+ * neighbour cell.  slopes / columns: device tables to build from (e.g. the gathered tables of a
+ * multi-GPU map), or both NULL for this handle's own map.  Synchronises the stream.
+ * adapter/gndt_twodmap_adapter.h (SlopeGraph) serves the planner from it.
+ */
+int gndt_build_edges(gndt_handle *h, const gndt_slope *slopes, size_t n_slopes, const gndt_column *columns,
+                     size_t n_columns, void *stream);
+/* offsets: n_slopes + 1 entries, targets: n_targets entries.  offsets == targets == NULL: size query only. */
+int gndt_copy_edges(gndt_handle *h, uint32_t *offsets, size_t cap_offsets, uint32_t *targets, size_t cap_targets,
+                    int dst_mem, size_t *n_slopes, size_t *n_targets);
 
 /*
  * Strip exchange through peer-mapped memory: the halo rows and the gather of the finished

@@ -574,6 +574,53 @@ int gndt_oracle_build(const float *xyz, size_t n, size_t stride_floats, const gn
   return GNDT_OK;
 }
 
+/* ------------------------------------------------------------------------------------
+ * The traversability graph: for every Slope the list TwoDmap::AccessibleNeighbors returns
+ * (map2D.h:530-548): countLRFB's four cells in the order left, right, forward, back, and in
+ * each cell the Slopes in std::map<int,Slope*> order (ascending z) that pass countReachable's
+ * tests (comand 2.5 / 4 and the checkList variant, :284-287,306-315).  Works from the
+ * canonical tables of a build; slope index = rank of the SLOPE voxel in table order.
+ * offsets has n_slopes + 1 entries.  Pinned against the reference's own AccessibleNeighbors
+ * inside oracle/_ref (ref_adapter_check.cpp, gndt_ref_graph_check).
+ * ---------------------------------------------------------------------------------- */
+#include "../include/gndt_lookup.h"
+int gndt_oracle_edges(const gndt_voxel *vox, size_t nv, const gndt_column *cols, size_t nc, const gndt_params *P,
+                      uint32_t **offsets_out, uint32_t **targets_out, size_t *n_slopes_out, size_t *n_targets_out) {
+  if (!vox || !cols || !P || !offsets_out || !targets_out) return GNDT_ERR_INVALID_ARG;
+  size_t ns = 0;
+  for (size_t v = 0; v < nv; ++v) ns += (vox[v].flags & GNDT_F_SLOPE) ? 1 : 0;
+  uint32_t *off = (uint32_t *)calloc(ns + 1, sizeof(uint32_t));
+  size_t cap = 4 * ns + 16, nt = 0;
+  uint32_t *tgt = (uint32_t *)malloc(cap * sizeof(uint32_t));
+  size_t i = 0;
+  for (size_t v = 0; v < nv; ++v) {
+    if (!(vox[v].flags & GNDT_F_SLOPE)) continue;
+    const gndt_voxel *c = &vox[v];
+    off[i++] = (uint32_t)nt;
+    for (int d = 0; d < 4; ++d) {
+      const int64_t col = gndtl_neighbor_column(cols, nc, c->sx, c->sy, d);
+      if (col < 0) continue;
+      for (uint32_t u = cols[col].voxel_begin; u < cols[col].voxel_begin + cols[col].voxel_count; ++u) {
+        const gndt_voxel *s = &vox[u];
+        if (!(s->flags & GNDT_F_SLOPE)) continue;
+        if (s->flags & GNDT_F_UP) continue;
+        if (!(s->rough <= P->rough_max)) continue;
+        if (!(count_angle(s->normal, c->normal) <= P->angle_max_deg)) continue;
+        float dz = s->mean[2] - c->mean[2];
+        if (!(fabsf(dz) <= P->reach_height)) continue;
+        if (nt == cap) { cap *= 2; tgt = (uint32_t *)realloc(tgt, cap * sizeof(uint32_t)); }
+        tgt[nt++] = s->slope;
+      }
+    }
+  }
+  off[ns] = (uint32_t)nt;
+  *offsets_out = off; *targets_out = tgt;
+  if (n_slopes_out) *n_slopes_out = ns;
+  if (n_targets_out) *n_targets_out = nt;
+  return GNDT_OK;
+}
+void gndt_oracle_free_edges(uint32_t *offsets, uint32_t *targets) { free(offsets); free(targets); }
+
 void gndt_oracle_free(oracle_result *R) {
   if (!R) return;
   free(R->voxels); free(R->columns); free(R->morton_list);

@@ -103,6 +103,25 @@ def ref_build(xyzw, params) -> OracleMap:
     return _run("ref", xyzw, params, 0)
 
 
+def oracle_edges(o: OracleMap, params: Params):
+    """(offsets[n_slopes + 1], targets): the AccessibleNeighbors lists of every Slope of an oracle
+    build (map2D.h:530-548), slope index = rank of the SLOPE voxel in table order."""
+    lib = _lib("port")
+    fn = lib.gndt_oracle_edges
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Params), C.POINTER(C.POINTER(C.c_uint32)),
+                   C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    fn.restype = C.c_int
+    off, tgt, ns, nt = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_size_t(), C.c_size_t()
+    vox, cols = np.ascontiguousarray(o.voxels), np.ascontiguousarray(o.columns)
+    rc = fn(vox.ctypes.data, len(vox), cols.ctypes.data, len(cols), C.byref(params), C.byref(off), C.byref(tgt), C.byref(ns), C.byref(nt))
+    assert rc == 0, rc
+    offsets = np.ctypeslib.as_array(off, (ns.value + 1,)).copy()
+    targets = np.ctypeslib.as_array(tgt, (max(nt.value, 1),)).copy()[: nt.value]
+    lib.gndt_oracle_free_edges.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.gndt_oracle_free_edges(off, tgt)
+    return offsets, targets
+
+
 # ---- key helpers -------------------------------------------------------------------------
 
 def oracle_count_morton(a, b):

@@ -117,3 +117,53 @@ extern "C" int gndt_ref_lookup_check(const float *origin, const gndt_params *P, 
   }
   return bad;
 }
+
+// ---- traversability graph (gndt_build_edges / oracle CSR) against the reference's own
+// AccessibleNeighbors for EVERY Slope (same Slopes, same order), and TwoDmap::computeCost against
+// the adapter's computeCostFast on two identical maps (same h on every Slope).
+//   out[0] reference AccessibleNeighbors calls/s   out[1] graph calls/s
+//   out[2] reference computeCost seconds           out[3] computeCostFast seconds
+//   out[4] Slopes with finite h                    out[5] traversable Slopes (computeCostFast's return)
+extern "C" int gndt_ref_graph_check(const float *origin, const gndt_params *P, const gndt_voxel *vox, size_t nv,
+                                    const gndt_slope *sl, size_t ns, const gndt_column *cols, size_t nc,
+                                    const uint32_t *off, const uint32_t *tgt, const float *goal, double *out) {
+  daysun::TwoDmap m1(P->grid_len, P->z_len), m2(P->grid_len, P->z_len);
+  m1.setInterval(P->slope_interval);
+  m2.setInterval(P->slope_interval);
+  gndt_adapter::fill_twodmap(m1, origin, vox, nv, sl, ns, cols, nc, false);
+  gndt_adapter::fill_twodmap(m2, origin, vox, nv, sl, ns, cols, nc, false);
+  gndt_adapter::SlopeGraph g1(m1, cols, nc, ns, off, tgt), g2(m2, cols, nc, ns, off, tgt);
+  int bad = 0;
+  for (size_t i = 0; i < ns; ++i) {
+    if (!g1.slope[i]) { ++bad; continue; }
+    std::list<Slope *> a = m1.AccessibleNeighbors(g1.slope[i], robot, 2.5f), b = g1.AccessibleNeighborsFast(g1.slope[i]);
+    if (a.size() != b.size() || !std::equal(a.begin(), a.end(), b.begin())) ++bad;
+  }
+  if (out) {
+    size_t n1 = 0, n2 = 0;
+    double t0 = now_s();
+    for (size_t i = 0; i < ns; ++i) n1 += m1.AccessibleNeighbors(g1.slope[i], robot, 2.5f).size();
+    double t1 = now_s();
+    for (size_t i = 0; i < ns; ++i) n2 += g1.AccessibleNeighborsFast(g1.slope[i]).size();
+    double t2 = now_s();
+    if (n1 != n2) ++bad;
+    out[0] = ns / (t1 - t0);
+    out[1] = ns / (t2 - t1);
+  }
+  if (goal) {
+    ros::Publisher pub, pub2;
+    const octomath::Vector3 gpos(goal[0], goal[1], goal[2]);
+    double t0 = now_s();
+    m1.computeCost(gpos, robot, pub, pub2, "slope");  // the reference's own cost map
+    double t1 = now_s();
+    const long n_trav = g2.computeCostFast(m2, gpos, robot);
+    double t2 = now_s();
+    size_t finite = 0;
+    for (size_t i = 0; i < ns; ++i) {
+      if (g1.slope[i]->h != g2.slope[i]->h) ++bad;
+      finite += g1.slope[i]->h < FLT_MAX;
+    }
+    if (out) { out[2] = t1 - t0; out[3] = t2 - t1; out[4] = (double)finite; out[5] = (double)n_trav; }
+  }
+  return bad;
+}

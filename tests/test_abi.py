@@ -48,7 +48,7 @@ def test_record_layouts_match_header():
     assert sizes[5] == _abi.VOXEL_DTYPE.fields["scatter"][1]
     assert sizes[6] == _abi.Params.max_voxels.offset
     assert sizes[7] == C.sizeof(_abi.Counts)
-    assert "GNDT_ABI_VERSION 1" in hdr
+    assert "GNDT_ABI_VERSION 2" in hdr
 
 
 def test_host_key_helpers_match_oracle():

@@ -104,3 +104,101 @@ def test_cell_center_and_origin():
         key, z = m.transMortonXYZ(c)
         assert z == int(v["sz"][i])
     m.close()
+
+
+def _touched_columns(scan, origin, gl):
+    """The reference's changeMorton_list for one scan (src/receiver.cpp:47-56): the (sx, sy) of the
+    scan's points in first-touched order, with the x-y index arithmetic of map2D.h:950-972 in binary32."""
+    def idx(v, o):
+        d = (np.abs(v - np.float32(o)) / np.float32(gl)).astype(np.float32)
+        n = np.maximum(np.ceil(d), 1).astype(np.int64)
+        return np.where(v > np.float32(o), n, -n)
+    sx, sy = idx(scan[:, 0], origin[0]), idx(scan[:, 1], origin[1])
+    seen, out = set(), []
+    for k in zip(sx.tolist(), sy.tolist()):
+        if k not in seen:
+            seen.add(k)
+            out.append(k)
+    return out
+
+
+def test_changed_columns_is_the_references_change_list():
+    _gpu()
+    from grid_ndt_b200 import TwoDmap
+    base = synthetic.cfg2(400_000, scale=0.2)
+    scans = list(synthetic.scans(3, 20_000, radius=4.0, cfg2_scale=0.2))
+    m = TwoDmap(0.2, 0.1)
+    m.setInterval(0.08)
+    m.chatterCallback(base, "slope")
+    for s in scans:
+        m.change2DMap(s)
+        cols = m.columns
+        got = [(int(c["sx"]), int(c["sy"])) for c in cols[m.changed_columns]]
+        want = _touched_columns(s, base[0, :3], 0.2)
+        assert got == want, (len(got), len(want))
+        assert m.changeMorton_list[0] == m.transMortonXYZ(s[0, :3])[0]
+    m.close()
+
+
+def test_remove_undoes_update():
+    """build(A) + update(B) + remove(B) == build(A): §8(f)4 (del2DMap, map2D.h:826-915)."""
+    _gpu()
+    from grid_ndt_b200 import TwoDmap
+    cloud = synthetic.cfg2(700_000, scale=0.25)
+    a, b = cloud[:450_000], cloud[450_000:]
+    m = TwoDmap(0.2, 0.1)
+    m.setInterval(0.08)
+    m.chatterCallback(a, "slope")
+    ref_v, ref_c = m.voxels.copy(), m.columns.copy()
+    m.change2DMap(b)
+    assert m.counts()["n_voxels"] > len(ref_v)
+    m.del2DMap(b)
+    v, c = m.voxels, m.columns
+    assert len(v) == len(ref_v) and len(c) == len(ref_c)
+    for f in ("sx", "sy", "sz", "count", "first_index", "column", "slope"):
+        assert np.array_equal(v[f], ref_v[f]), f
+    assert m.counts()["n_input"] == 450_000 and m.counts()["n_binned"] == 449_999
+    # the full parity bar against the oracle's build of A alone (floats differ from the GPU's own
+    # build of A only by the rounding of the merge and its inverse)
+    _check_against_batch(m, a, default_params(0.2, 0.1, 0.08))
+    touched = {(int(x["sx"]), int(x["sy"])) for x in c[m.changed_columns]}
+    want = set(_touched_columns(b, a[0, :3], 0.2)) & {(int(x["sx"]), int(x["sy"])) for x in c}
+    assert touched == want  # cells that vanished with the scan are not listed
+    m.close()
+
+
+def test_failed_update_and_remove_leave_the_map_unchanged():
+    """a capacity overflow used to leave the resident map half-fused."""
+    _gpu()
+    from grid_ndt_b200 import GndtError, TwoDmap
+    cloud = synthetic.cfg2(500_000, scale=0.22)
+    a, b = cloud[:300_000], cloud[300_000:]
+    m = TwoDmap(0.2, 0.1)
+    m.setInterval(0.08)
+    m.chatterCallback(a, "slope")
+    n0 = m.counts()["n_voxels"]
+    m.close()
+    m = TwoDmap(0.2, 0.1)
+    m.setInterval(0.08)
+    m.params.max_voxels = n0 + 10  # room for the map of A, not for A + B
+    m.chatterCallback(a, "slope")
+    before = (m.voxels.tobytes(), m.slopes.tobytes(), m.columns.tobytes(), m.counts())
+    m.change2DMap(b)
+    with pytest.raises(GndtError) as e:
+        m.counts()
+    assert e.value.status == _abi.GNDT_ERR_CAPACITY
+    assert (m.voxels.tobytes(), m.slopes.tobytes(), m.columns.tobytes(), m.counts()) == before
+    m.del2DMap(b)  # never fused
+    with pytest.raises(GndtError) as e:
+        m.counts()
+    assert e.value.status == _abi.GNDT_ERR_STATE
+    assert (m.voxels.tobytes(), m.slopes.tobytes(), m.columns.tobytes(), m.counts()) == before
+    m.params.max_voxels = 0
+    # changing the cell size under a resident map is refused (two key spaces cannot be fused)
+    m.setLen(0.3)
+    import ctypes as C
+    from grid_ndt_b200 import lib
+    lib().gndt_set_params(m._h, C.byref(m.params))
+    with pytest.raises(GndtError):
+        m.change2DMap(b)
+    m.close()
