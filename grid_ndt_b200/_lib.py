@@ -72,6 +72,14 @@ SYMBOLS = {
     "gndt_xchg_connect": (_i, [_vp, C.POINTER(XchgInfo), _i]),
     "gndt_xchg_run": (_i, [_vp, _vp]),
     "gndt_xchg_view_get": (_i, [_vp, C.POINTER(XchgView)]),
+    "gndt_multi_create": (_i, [C.POINTER(Params), C.POINTER(C.c_int), _i, _sz, _sz, _i, C.POINTER(_vp)]),
+    "gndt_multi_destroy": (_i, [_vp]),
+    "gndt_multi_build": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "gndt_multi_update": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "gndt_multi_view": (_i, [_vp, _i, C.POINTER(XchgView)]),
+    "gndt_multi_cuts": (_i, [_vp, C.POINTER(C.c_int32), _i]),
+    "gndt_multi_handle": (_vp, [_vp, _i]),
+    "gndt_multi_last_error": (C.c_char_p, [_vp]),
     "gndt_plan_tiles": (_i, [_vp, _vp, _sz, _sz, _i, _i, C.POINTER(C.c_int32), _vp]),
     "gndt_set_stage_timing": (_i, [_vp, _i]),
     "gndt_stage_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "gndt_device.cuh"
 #include "gndt_lookup.h"
@@ -51,7 +52,7 @@ struct gndt_handle {
   // workspace sized by points
   Buffer in_stage, buf_a, buf_b, zero;
   // workspace sized by voxels
-  Buffer mom, mom_alt, table, slopes, columns, vfirst;
+  Buffer mom, mom_alt, table, slopes, columns, vfirst, slope_col;
   // PointCloud2 ingest: pinned staging ring for pageable messages, repacked points for odd layouts
   void *ring = nullptr;
   cudaEvent_t ring_ev[4] = {};
@@ -282,6 +283,7 @@ int reserve(gndt_handle *h, size_t n, size_t cap_vox, bool host_input, size_t st
   if ((rc = ensure(h, h->slopes, cap_vox * sizeof(gndt_slope))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->columns, cap_vox * sizeof(gndt_column))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->vfirst, cap_vox * sizeof(u32))) != GNDT_OK) return rc;
+  if ((rc = ensure(h, h->slope_col, cap_vox * sizeof(u32))) != GNDT_OK) return rc;
   if ((rc = ensure(h, h->small, 256)) != GNDT_OK) return rc;
   h->cap_points = n;
   h->cap_voxels = cap_vox;
@@ -424,14 +426,14 @@ __global__ void table_bounds_kernel(Ctl *ctl, const gndt_voxel *table, u32 n_fix
 int back_end(gndt_handle *h, cudaStream_t st, const DevParams &dp, const VoxMoments *mom, bool bounds_from_table) {
   const int g_lab = grid_for(h, h->cap_voxels, kLabelThreads, 8);
   launch(h, finalize_label_kernel, g_lab, kFinThreads, sizeof(FinSmem), st, h->ctl, mom, (gndt_voxel *)h->table.p,
-         (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p, (u32 *)h->vfirst.p, h->blk_state, h->blk_groups,
+         (gndt_slope *)h->slopes.p, (gndt_column *)h->columns.p, (u32 *)h->vfirst.p, (u32 *)h->slope_col.p, h->blk_state, h->blk_groups,
          &h->ctl->ticket[7], dp);
   if (bounds_from_table) launch(h, table_bounds_kernel, 1, 32, 0, st, h->ctl, (const gndt_voxel *)h->table.p, 0u);
   launch(h, column_finish_kernel, g_lab, 256, 0, st, h->ctl, (const gndt_voxel *)h->table.p, (const u32 *)h->vfirst.p, 0u,
          (gndt_column *)h->columns.p, h->row_start, h->row_end, 0, 0);
   if (h->stage_timing) GNDT_CUDA(h, cudaEventRecord(h->ev[EV_LABEL], st));
   launch(h, edges_kernel, g_lab, 256, 0, st, h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p,
-         (const gndt_column *)h->columns.p, (const u32 *)h->row_start, (const u32 *)h->row_end, 0, 0, 0, dp);
+         (const gndt_column *)h->columns.p, (const u32 *)h->slope_col.p, (const u32 *)h->row_start, (const u32 *)h->row_end, 0, 0, 0, dp);
   GNDT_CUDA(h, cudaEventRecord(h->ev[EV_EDGES], st));
   return GNDT_OK;
 }
@@ -511,7 +513,7 @@ int gndt_destroy(gndt_handle *h) {
     if (h->x_opened[r]) cudaIpcCloseMemHandle(h->x_opened[r]);
   if (h->ring) { cudaFreeHost(h->ring); for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]); }
   Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
-                    &h->columns, &h->vfirst, &h->mom_scan, &h->upd_work, &h->msg_points, &h->small, &h->lookback, &h->f_zero, &h->xbuf, &h->g_work, &h->g_off, &h->g_tgt};
+                    &h->columns, &h->vfirst, &h->slope_col, &h->mom_scan, &h->upd_work, &h->msg_points, &h->small, &h->lookback, &h->f_zero, &h->xbuf, &h->g_work, &h->g_off, &h->g_tgt};
   for (Buffer *b : bufs) if (b->p) cudaFree(b->p);
   for (int i = 0; i < EV_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -1119,6 +1121,140 @@ int gndt_xchg_view_get(gndt_handle *h, gndt_xchg_view *out) {
     out->n_columns += c[1];
     out->n_slopes += c[2];
   }
+  return GNDT_OK;
+}
+
+// ---- one process, several GPUs (what the reference's single receiver process would call) ----
+struct gndt_multi {
+  std::vector<gndt_handle *> h;
+  std::vector<int> dev;
+  std::vector<cudaStream_t> st;
+  std::vector<Buffer> cloud;   // every GPU's copy of the current cloud / scan
+  std::vector<int32_t> cuts;
+  gndt_params params;
+  bool planned = false;
+  std::string err;
+};
+
+static int multi_fail(gndt_multi *m, int i, int rc, const char *what) {
+  m->err = std::string(what) + " (device index " + std::to_string(i) + "): " + (i >= 0 && i < (int)m->h.size() && m->h[i] ? m->h[i]->err : g_create_error);
+  return rc;
+}
+
+int gndt_multi_create(const gndt_params *params, const int *devices, int ndev, size_t cap_records, size_t cap_halo_records, int what,
+                      gndt_multi **out) {
+  if (!out || !params || !devices || ndev < 1 || ndev > kMaxRanks) return GNDT_ERR_INVALID_ARG;
+  *out = nullptr;
+  gndt_multi *m = new gndt_multi();
+  m->params = *params;
+  m->h.assign(ndev, nullptr);
+  m->dev.assign(devices, devices + ndev);
+  m->st.assign(ndev, nullptr);
+  m->cloud.resize(ndev);
+  std::vector<gndt_xchg_info> info(ndev);
+  for (int i = 0; i < ndev; ++i) {
+    int rc = gndt_create(params, devices[i], &m->h[i]);
+    if (rc == GNDT_OK && cudaStreamCreateWithFlags(&m->st[i], cudaStreamNonBlocking) != cudaSuccess) rc = GNDT_ERR_CUDA;
+    if (rc == GNDT_OK) rc = gndt_xchg_create(m->h[i], i, ndev, cap_records, cap_halo_records, what, &info[i]);
+    if (rc != GNDT_OK) { g_create_error = "gndt_multi_create: device " + std::to_string(devices[i]) + ": " + (m->h[i] ? m->h[i]->err : g_create_error); gndt_multi_destroy(m); return rc; }
+  }
+  for (int i = 0; i < ndev; ++i) {
+    const int rc = gndt_xchg_connect(m->h[i], info.data(), ndev);
+    if (rc != GNDT_OK) { g_create_error = "gndt_multi_create: " + m->h[i]->err; gndt_multi_destroy(m); return rc; }
+  }
+  *out = m;
+  return GNDT_OK;
+}
+
+int gndt_multi_destroy(gndt_multi *m) {
+  if (!m) return GNDT_ERR_INVALID_ARG;
+  for (size_t i = 0; i < m->h.size(); ++i) {
+    if (!m->h[i]) continue;
+    cudaSetDevice(m->dev[i]);
+    cudaDeviceSynchronize();
+    if (m->cloud[i].p) cudaFree(m->cloud[i].p);
+    if (m->st[i]) cudaStreamDestroy(m->st[i]);
+    gndt_destroy(m->h[i]);
+  }
+  delete m;
+  return GNDT_OK;
+}
+
+const char *gndt_multi_last_error(const gndt_multi *m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+gndt_handle *gndt_multi_handle(gndt_multi *m, int index) { return (m && index >= 0 && index < (int)m->h.size()) ? m->h[index] : nullptr; }
+
+// every GPU gets the whole cloud: host input goes up each GPU's own PCIe link, device input (on GPU 0) fans out over NVLink
+static int multi_stage(gndt_multi *m, const void *xyz, size_t n, size_t stride_bytes, int mem) {
+  const size_t bytes = n * stride_bytes;
+  for (size_t i = 0; i < m->h.size(); ++i) {
+    gndt_handle *h = m->h[i];
+    if (cudaSetDevice(m->dev[i]) != cudaSuccess) return multi_fail(m, (int)i, GNDT_ERR_CUDA, "cudaSetDevice");
+    if (mem == GNDT_MEM_DEVICE && i == 0) continue;  // already there
+    int rc = ensure(h, m->cloud[i], bytes);
+    if (rc != GNDT_OK) return multi_fail(m, (int)i, rc, "cloud staging");
+    cudaError_t e = mem == GNDT_MEM_HOST ? cudaMemcpyAsync(m->cloud[i].p, xyz, bytes, cudaMemcpyHostToDevice, m->st[i])
+                                         : cudaMemcpyPeerAsync(m->cloud[i].p, m->dev[i], xyz, m->dev[0], bytes, m->st[i]);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return multi_fail(m, (int)i, GNDT_ERR_CUDA, "cloud copy"); }
+  }
+  return GNDT_OK;
+}
+static const void *multi_cloud(gndt_multi *m, size_t i, const void *xyz, int mem) { return (mem == GNDT_MEM_DEVICE && i == 0) ? xyz : m->cloud[i].p; }
+
+int gndt_multi_build(gndt_multi *m, const void *xyz, size_t n, size_t stride_bytes, int mem) {
+  if (!m || !xyz || n == 0) return GNDT_ERR_INVALID_ARG;
+  const int nd = (int)m->h.size();
+  int rc = multi_stage(m, xyz, n, stride_bytes, mem);
+  if (rc != GNDT_OK) return rc;
+  // balanced x strips from GPU 0's histogram of the cloud's x columns; the origin is the same on every GPU
+  cudaSetDevice(m->dev[0]);
+  m->cuts.assign(nd + 1, 0);
+  gndt_params p0 = m->params;
+  p0.tile_lo = p0.tile_hi = 0;
+  if ((rc = gndt_set_params(m->h[0], &p0)) != GNDT_OK) return multi_fail(m, 0, rc, "set_params");
+  if ((rc = gndt_plan_tiles(m->h[0], multi_cloud(m, 0, xyz, mem), n, stride_bytes, GNDT_MEM_DEVICE, nd, m->cuts.data(), m->st[0])) != GNDT_OK)
+    return multi_fail(m, 0, rc, "gndt_plan_tiles");
+  m->planned = true;
+  for (int i = 0; i < nd; ++i) {
+    cudaSetDevice(m->dev[i]);
+    gndt_params p = m->params;
+    const bool empty = nd > 1 && m->cuts[i] >= m->cuts[i + 1];
+    p.tile_lo = nd == 1 ? 0 : (empty ? GNDT_MAX_INDEX : m->cuts[i]);
+    p.tile_hi = nd == 1 ? 0 : (empty ? GNDT_MAX_INDEX + 1 : m->cuts[i + 1]);
+    if ((rc = gndt_set_params(m->h[i], &p)) != GNDT_OK) return multi_fail(m, i, rc, "set_params");
+    if ((rc = gndt_build(m->h[i], multi_cloud(m, i, xyz, mem), n, stride_bytes, GNDT_MEM_DEVICE, m->st[i])) != GNDT_OK) return multi_fail(m, i, rc, "gndt_build");
+    if ((rc = gndt_xchg_run(m->h[i], m->st[i])) != GNDT_OK) return multi_fail(m, i, rc, "gndt_xchg_run");
+  }
+  return GNDT_OK;
+}
+
+int gndt_multi_update(gndt_multi *m, const void *xyz, size_t n, size_t stride_bytes, int mem) {
+  if (!m || !xyz || n == 0) return GNDT_ERR_INVALID_ARG;
+  if (!m->planned) { m->err = "gndt_multi_update: no map has been built"; return GNDT_ERR_STATE; }
+  int rc = multi_stage(m, xyz, n, stride_bytes, mem);
+  if (rc != GNDT_OK) return rc;
+  for (size_t i = 0; i < m->h.size(); ++i) {  // every GPU keeps the points of its strip
+    cudaSetDevice(m->dev[i]);
+    if ((rc = gndt_update(m->h[i], multi_cloud(m, i, xyz, mem), n, stride_bytes, GNDT_MEM_DEVICE, m->st[i])) != GNDT_OK) return multi_fail(m, (int)i, rc, "gndt_update");
+    if ((rc = gndt_xchg_run(m->h[i], m->st[i])) != GNDT_OK) return multi_fail(m, (int)i, rc, "gndt_xchg_run");
+  }
+  return GNDT_OK;
+}
+
+int gndt_multi_view(gndt_multi *m, int index, gndt_xchg_view *out) {
+  if (!m || !out || index < 0 || index >= (int)m->h.size()) return GNDT_ERR_INVALID_ARG;
+  // a failure on one strip shows up as a watchdog on the others: report the first real error
+  for (size_t i = 0; i < m->h.size(); ++i) {
+    cudaSetDevice(m->dev[i]);
+    gndt_xchg_view v;
+    const int rc = gndt_xchg_view_get(m->h[i], (int)i == index ? out : &v);
+    if (rc != GNDT_OK) return multi_fail(m, (int)i, rc, "exchange");
+  }
+  return GNDT_OK;
+}
+
+int gndt_multi_cuts(gndt_multi *m, int32_t *cuts, int cap) {
+  if (!m || !cuts || cap < (int)m->cuts.size()) return GNDT_ERR_INVALID_ARG;
+  std::copy(m->cuts.begin(), m->cuts.end(), cuts);
   return GNDT_OK;
 }
 

@@ -49,7 +49,8 @@ struct __align__(128) FinSmem {
 constexpr int kFinThreads = kLabelThreads + 32;
 __global__ void __launch_bounds__(kFinThreads, GNDT_FIN_MINBLOCKS)
 finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_slope *slopes,
-                      gndt_column *columns, u32 *vfirst, u64 *blk_state, GroupState *blk_groups, u32 *counters, DevParams P) {
+                      gndt_column *columns, u32 *vfirst, u32 *slope_col, u64 *blk_state, GroupState *blk_groups, u32 *counters,
+                      DevParams P) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_fin[];
@@ -193,6 +194,7 @@ finalize_label_kernel(Ctl *ctl, const VoxMoments *mom, gndt_voxel *table, gndt_s
           d[0] = make_float4(r0.x, r0.y, r0.z, r1.y);        // sx sy sz mean.x
           d[1] = make_float4(r1.z, r1.w, r4.y, r4.z);        // mean.y mean.z normal.x normal.y
           d[2] = make_float4(r4.w, last.x, __uint_as_float(flags), __uint_as_float(v));
+          slope_col[slopes_before] = col_idx;  // compact: the edge kernel need not touch the 96-byte record for it
         }
         if (head) {
           float4 *d = reinterpret_cast<float4 *>(columns + col_idx);
@@ -283,7 +285,7 @@ __device__ __forceinline__ bool cell_reachable(const gndt_column &c, const gndt_
 // Index arithmetic is in contiguous space, which is countLRFB's quadrant crossing
 // (x==1 / y==1 cases, map2D.h:219-253) without the special cases.
 __global__ void __launch_bounds__(256)
-edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column *columns,
+edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column *columns, const u32 *slope_col,
              const u32 *row_start, const u32 *row_end, int cx_base_fixed, int cx_max_fixed, int use_fixed,
              DevParams P) {
   pdl_wait();
@@ -294,7 +296,7 @@ edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gndt_column 
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
     gndt_slope me = slopes[i];
     const int cx = contiguous_index(me.sx), cy = contiguous_index(me.sy);
-    const u32 ci = table[me.voxel].column;
+    const u32 ci = slope_col[i];
     const float n[3] = {me.normal[0], me.normal[1], me.normal[2]};
     const double n_len = normal_length(n);
     u32 bits = 0;

@@ -338,6 +338,28 @@ int gndt_xchg_run(gndt_handle *h, void *stream);
 int gndt_xchg_view_get(gndt_handle *h, gndt_xchg_view *out);
 
 /*
+ * One process, several GPUs: the form the reference's receiver (one C++ process, ros::spin,
+ * src/receiver.cpp:283) would call.  gndt_multi_create makes one builder per device and
+ * connects their exchange buffers; gndt_multi_build takes ONE cloud (host memory, or device
+ * memory of devices[0]), plans balanced x strips, gives every GPU the cloud (host: each GPU's
+ * own PCIe link; device: NVLink fan-out), builds the strips and runs the exchange, all
+ * asynchronously on one private stream per device.  gndt_multi_view(index) then waits for it and
+ * returns the tables of the WHOLE map as they lie on GPU `index` (any of them: all are equal).
+ * gndt_multi_update fuses one more scan (every GPU keeps the points of its strip).
+ * gndt_multi_handle gives the per-device builder (counts, stage times, strip-local tables).
+ */
+typedef struct gndt_multi gndt_multi;
+int gndt_multi_create(const gndt_params *params, const int *devices, int ndev, size_t cap_records,
+                      size_t cap_halo_records, int what, gndt_multi **out);
+int gndt_multi_destroy(gndt_multi *m);
+int gndt_multi_build(gndt_multi *m, const void *xyz, size_t n, size_t stride_bytes, int mem);
+int gndt_multi_update(gndt_multi *m, const void *xyz, size_t n, size_t stride_bytes, int mem);
+int gndt_multi_view(gndt_multi *m, int index, gndt_xchg_view *out);
+int gndt_multi_cuts(gndt_multi *m, int32_t *cuts, int cap); /* ndev + 1 strip boundaries of the last build */
+gndt_handle *gndt_multi_handle(gndt_multi *m, int index);
+const char *gndt_multi_last_error(const gndt_multi *m);
+
+/*
  * Balanced x strips for `ntiles` GPUs: cuts[0..ntiles] in contiguous signed x index
  * space such that strip t = [cuts[t], cuts[t+1]) holds ~n/ntiles points.  Every rank
  * that passes the same cloud gets the same cuts (no communication needed).
