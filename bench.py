@@ -148,8 +148,10 @@ def make_cloud(rank):
     from grid_ndt_b200 import synthetic
     cloud = synthetic.cfg2(POINTS_PER_GPU)
     if rank:
-        nz = np.abs(cloud[:, :3]).sum(axis=1) > 0  # the (0,0,0) padding stays where it is
-        cloud[nz, 0] += np.float32(SCENE_W * rank)
+        # the whole scene moves, its (0,0,0) padding included: every strip keeps one pathologically heavy voxel at
+        # ITS sensor origin and the same extent (leaving the padding at the global origin stretched the bounding
+        # box of every strip but the first over the whole map, costing those strips a partition pass)
+        cloud[:, 0] += np.float32(SCENE_W * rank)
     return cloud
 
 
@@ -415,20 +417,32 @@ def main():
     # ---- end to end: pinned host cloud in, result tables out (into pinned host buffers), every step
     m.pin_results(True)
     if world > 1:
-        pin = {}
+        # The host planner is one consumer: the whole map must reach ONE host buffer.  Every rank copies ITS strip
+        # of the gathered Slope + Cell tables (indices already global) into a buffer shared by all ranks (POSIX
+        # shared memory, page-locked in every process), so the read-back uses all N PCIe links instead of rank 0's.
+        from multiprocessing import shared_memory
+        cap_rec = cap
+        shm_bytes = cap_rec * (48 + 32)
+        name = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=shm_bytes)
+            name[0] = shm.name
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        host_map = torch.from_numpy(np.ndarray((shm_bytes,), np.uint8, buffer=shm.buf))
+        assert int(torch.cuda.cudart().cudaHostRegister(host_map.data_ptr(), shm_bytes, 0)) == 0
+        col_base = cap_rec * 48
 
         def read_back(g):
-            """rank 0: the gathered Slope + Cell tables of the whole map -> pinned host memory."""
-            if rank != 0:
-                return 0
-            total = 0
-            for name, t in (("slopes", g.slopes), ("columns", g.columns)):
-                if name not in pin or pin[name].numel() < t.numel():
-                    pin[name] = torch.empty(int(t.numel() * 1.2) + 4096, dtype=torch.uint8).pin_memory()
-                pin[name][: t.numel()].copy_(t.reshape(-1), non_blocking=True)
-                total += t.numel()
+            """this rank's strip of the gathered tables -> the shared host map; returns the bytes it moved"""
+            sc = g.strip_counts
+            s0, s1 = int(sc[:rank, 2].sum()) * 48, int(sc[:rank + 1, 2].sum()) * 48
+            c0, c1 = int(sc[:rank, 1].sum()) * 32, int(sc[:rank + 1, 1].sum()) * 32
+            host_map[s0:s1].copy_(g.slopes.reshape(-1)[s0:s1], non_blocking=True)
+            host_map[col_base + c0: col_base + c1].copy_(g.columns.reshape(-1)[c0:c1], non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return total
+            return (s1 - s0) + (c1 - c0)
 
         def e2e_step():
             return read_back(step(host))
@@ -476,14 +490,23 @@ def main():
                 if i + 1 < n:
                     tmp.submit(host, "slope", origin=origin, cuts=None, filter_points=False)
                 got = read_back(tmp.collect())
-                assert rank != 0 or got == d2h, (got, d2h)
+                assert got == d2h, (got, d2h)
             tmp.synchronize()
         piped(3)
         e2e_s = wall(piped, n_e2e)
-        e2e_mode = (f"TiledTwoDmap depth {tmp.depth}, host input on every rank: H2D of cloud i+1 overlaps the exchange of cloud i; rank 0 reads back "
-                    "the gathered Slope + Cell tables of the whole map (the host planner's input); the other ranks keep theirs on the GPU")
+        e2e_mode = (f"TiledTwoDmap depth {tmp.depth}, host input on every rank: H2D of cloud i+1 overlaps the exchange of cloud i; the gathered Slope + Cell "
+                    "tables of the WHOLE map (the host planner's input) land in one host buffer shared by all ranks, each rank copying its own strip "
+                    "over its own PCIe link; d2h_bytes_per_step is the whole map")
     e2e_value = total_pts / e2e_s
-    d2h = int(max_over_ranks(float(d2h)))
+    if world > 1:
+        t = torch.tensor([float(d2h)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        d2h = int(t.item())
+        torch.cuda.cudart().cudaHostUnregister(host_map.data_ptr())
+        del host_map
+        shm.close()
+        if rank == 0:
+            shm.unlink()
 
     peak, peak_src = measured_peak()
     v_tab = counts["n_voxels"]
@@ -529,7 +552,7 @@ def main():
                      "what": "whole build (all kernels of one step) on one GPU, one build at a time: (16 B x points + 96 B x voxels) / "
                              "device time of the build (library start/end events); achieved_in_flight = the same bytes / ms_per_step of the timed "
                              "region (two builds in flight); peak = " + peak_src},
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_pts * 16), "d2h_bytes_per_step": int(d2h),
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_pts * 16 * world), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "mode": e2e_mode, "serial_ms_per_step": serial_s * 1e3,
                 "h2d_gbs_per_gpu_if_copy_bound": n_pts * 16 / e2e_s / 1e9},
         "gpu_launches": launches,

@@ -98,6 +98,10 @@ struct gndt_handle {
   XPeers xp = {};
   void *x_opened[kMaxRanks] = {};  // cudaIpcOpenMemHandle mappings to close
   int x_what = 0;
+  int x_spare_ctas = 0;            // CTA slots the partition passes leave to the exchange (GNDT_XCHG_SPARE; measured: no gain)
+  int x_push_ctas = 48;            // grid of the push kernel (GNDT_XCHG_CTAS), 256 threads each
+  cudaStream_t x_stream = nullptr; // high-priority stream of the push: it takes the first slots that free up
+  cudaEvent_t x_ev[2] = {};
   u32 x_epoch = 0;
   bool x_created = false, x_connected = false;
   // state
@@ -391,8 +395,11 @@ int front_end(gndt_handle *h, cudaStream_t st, const float *d_in, size_t n, size
   // the division mode is a template argument (two instantiations), not a run-time select
   auto *first_pass = dp.fast_div ? sort_pass_kernel<true, true> : sort_pass_kernel<true, false>;
   auto *next_pass = dp.fast_div ? sort_pass_kernel<false, true> : sort_pass_kernel<false, false>;
-  const int g0 = (int)std::min<size_t>(tiles, (size_t)h->sm_count * h->sort_ctas_per_sm[0]);
-  const int g1 = (int)std::min<size_t>(tiles, (size_t)h->sm_count * h->sort_ctas_per_sm[1]);
+  // With a strip exchange attached, a few CTA slots stay free: the persistent passes would otherwise hold every
+  // SM for 60 % of a build and the exchange of the previous build (another stream) could not run beside them.
+  const size_t spare = h->x_created ? (size_t)h->x_spare_ctas : 0;
+  const int g0 = (int)std::min<size_t>(tiles, std::max<size_t>((size_t)h->sm_count * h->sort_ctas_per_sm[0], spare + 1) - spare);
+  const int g1 = (int)std::min<size_t>(tiles, std::max<size_t>((size_t)h->sm_count * h->sort_ctas_per_sm[1], spare + 1) - spare);
   launch(h, first_pass, g0, kSortThreads, sizeof(SortSmem), st, h->ctl, 0, d_in, stride_f, n, start, (const float4 *)nullptr, A,
          h->lb[0], h->glb[0], h->lb[1], h->glb[1], h->hist, dp);
   for (int p = 1; p < kMaxPasses; ++p) {
@@ -511,6 +518,7 @@ int gndt_destroy(gndt_handle *h) {
   cudaSetDevice(h->device);
   for (int r = 0; r < kMaxRanks; ++r)
     if (h->x_opened[r]) cudaIpcCloseMemHandle(h->x_opened[r]);
+  if (h->x_stream) { cudaStreamDestroy(h->x_stream); for (int i = 0; i < 2; ++i) if (h->x_ev[i]) cudaEventDestroy(h->x_ev[i]); }
   if (h->ring) { cudaFreeHost(h->ring); for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]); }
   Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
                     &h->columns, &h->vfirst, &h->slope_col, &h->mom_scan, &h->upd_work, &h->msg_points, &h->small, &h->lookback, &h->f_zero, &h->xbuf, &h->g_work, &h->g_off, &h->g_tgt};
@@ -1017,6 +1025,14 @@ int gndt_xchg_create(gndt_handle *h, int rank, int world, size_t cap_records, si
   h->x_epoch = 0;
   h->x_created = true;
   h->x_connected = false;
+  if (const char *e = getenv("GNDT_XCHG_SPARE")) h->x_spare_ctas = std::max(0, atoi(e));
+  if (const char *e = getenv("GNDT_XCHG_CTAS")) h->x_push_ctas = std::max(1, atoi(e));
+  if (!h->x_stream) {
+    int lo_p = 0, hi_p = 0;
+    GNDT_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    GNDT_CUDA(h, cudaStreamCreateWithPriority(&h->x_stream, cudaStreamNonBlocking, hi_p));
+    for (int i = 0; i < 2; ++i) GNDT_CUDA(h, cudaEventCreateWithFlags(&h->x_ev[i], cudaEventDisableTiming));
+  }
   memset(mine, 0, sizeof(*mine));
   cudaIpcMemHandle_t ipc;
   GNDT_CUDA(h, cudaIpcGetMemHandle(&ipc, h->xbuf.p));
@@ -1079,17 +1095,26 @@ int gndt_xchg_run(gndt_handle *h, void *stream) {
   u32 *done_counter = reinterpret_cast<u32 *>(static_cast<char *>(h->small.p) + 192);
   const DevParams dp = make_dev(h, h->params, h->cap_voxels);
   unsigned char *mine = X.buf[X.rank];
+  static const int skip = [] { const char *e = getenv("GNDT_XCHG_SKIP"); return e ? atoi(e) : 0; }();  // diagnosis only
+  if (skip & 4) return GNDT_OK;
   xchg_publish_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch);
+  if (!(skip & 1)) {
   xchg_halo_send_kernel<<<2, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_column *)h->columns.p, h->row_start,
                                            h->row_end, X, L, epoch);
   xchg_halo_wait_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch, have);
   xchg_halo_edges_kernel<<<grid_for(h, h->cap_voxels, 256, 4), 256, 0, st>>>(
       h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p, reinterpret_cast<const gndt_voxel *>(mine + L.halo[0]),
       reinterpret_cast<const gndt_voxel *>(mine + L.halo[1]), have, dp);
-  static const int push_ctas = [] { const char *e = getenv("GNDT_XCHG_CTAS"); return e ? std::max(1, atoi(e)) : 0; }();
-  xchg_push_kernel<<<push_ctas ? push_ctas : 48, 512, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_slope *)h->slopes.p,
-                                                (const gndt_column *)h->columns.p, X, L, h->x_what, epoch, done_counter);
-  xchg_wait_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch);
+  }
+  if (skip & 2) return GNDT_OK;
+  // the bulk transfer and the final wait run on the high-priority stream, fenced by events on both sides
+  GNDT_CUDA(h, cudaEventRecord(h->x_ev[0], st));
+  GNDT_CUDA(h, cudaStreamWaitEvent(h->x_stream, h->x_ev[0], 0));
+  xchg_push_kernel<<<h->x_push_ctas, kPushThreads, 0, h->x_stream>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_slope *)h->slopes.p,
+                                                            (const gndt_column *)h->columns.p, X, L, h->x_what, epoch, done_counter);
+  xchg_wait_kernel<<<1, 32, 0, h->x_stream>>>(h->ctl, X, L, epoch);
+  GNDT_CUDA(h, cudaEventRecord(h->x_ev[1], h->x_stream));
+  GNDT_CUDA(h, cudaStreamWaitEvent(st, h->x_ev[1], 0));
   h->launches += 6;
   h->counts_valid = false;
   h->last_stream = st;

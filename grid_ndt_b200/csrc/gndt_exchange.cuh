@@ -207,7 +207,7 @@ xchg_halo_edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gn
 template <int KIND>  // 0 voxels, 1 slopes, 2 columns
 __device__ __forceinline__ void push_table(const uint4 *src, size_t n_chunks, size_t dst_off_bytes, size_t first_chunk, const XPeers &X,
                                            const u32 off[3]) {
-  constexpr int kU = 4;
+  constexpr int kU = 8;
   constexpr u32 kPer = KIND == 0 ? 6u : (KIND == 1 ? 3u : 2u);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_chunks; i0 += kU * stride) {
@@ -230,7 +230,8 @@ __device__ __forceinline__ void push_table(const uint4 *src, size_t n_chunks, si
   }
 }
 
-__global__ void __launch_bounds__(512)
+constexpr int kPushThreads = 256;  // small CTAs: they must fit beside a resident partition-pass CTA (half the register file)
+__global__ void __launch_bounds__(kPushThreads, 2)
 xchg_push_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_slope *slopes, const gndt_column *columns, XPeers X, XLayout L,
                  int what, u32 epoch, u32 *done_counter) {
   const XMail *mine = reinterpret_cast<const XMail *>(X.buf[X.rank] + L.mail);

@@ -113,6 +113,7 @@ class TiledTwoDmap:
             # size exchange of build i+1 (collective: every rank constructs its TiledTwoDmap)
             self.gather_group = dist.new_group(ranks=list(range(world))) if group is None else dist.new_group(
                 ranks=dist.get_process_group_ranks(group))
+        self.build_stream = None
         self.map = self.slots[0].map
         self.device = self.slots[0].device
         self._next = 0
@@ -173,6 +174,8 @@ class TiledTwoDmap:
                 m.setTile(*((lo, hi) if lo < hi else _abi.TILE_EMPTY))
             else:
                 m.setTile(0, 0)
+        if self.exchange == "native" and self.depth > 1:
+            return self._submit_pipelined(s, cloud, demand)
         stream = s.stream if s.stream is not None else torch.cuda.current_stream(s.device)
         if s.stream is not None:
             s.stream.wait_stream(torch.cuda.current_stream(s.device))  # the cloud was produced there
@@ -207,6 +210,43 @@ class TiledTwoDmap:
             _check(m._h, L.gndt_device_count_ptr(m._h, C.byref(p_cnt)))
             mine = _as_tensor(p_cnt.value, 16, s.device).view(torch.int32)
             dist.all_gather_into_tensor(s.counts, mine, group=self.group)
+        self._inflight.append(s)
+        return s
+
+    def _submit_pipelined(self, s, cloud, demand):
+        """depth > 1, native exchange.  Builds run ONE AFTER THE OTHER on a shared build stream (three builds
+        time-slicing the SMs would all finish late and their exchanges would then pile up behind them); what
+        overlaps is the exchange of build i (this builder's own stream, NVLink-bound, few SMs) with the kernels of
+        build i + 1, and the upload of a host cloud (this builder's stream as well) with everything before it."""
+        m, L = s.map, lib()
+        if self.build_stream is None:
+            self.build_stream = torch.cuda.Stream(s.device)
+            for t in self.slots:
+                t.build_done, t.xchg_done, t.staged = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+                t.dev_cloud = None
+        bs = self.build_stream
+        cur = torch.cuda.current_stream(s.device)
+        if isinstance(cloud, torch.Tensor) and cloud.is_cuda:
+            bs.wait_stream(cur)  # the cloud was produced there
+            src = cloud
+        else:  # host cloud: upload on the builder's own stream, beside the builds in flight
+            host = cloud if isinstance(cloud, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cloud, dtype=np.float32))
+            if s.dev_cloud is None or s.dev_cloud.shape != host.shape:
+                s.dev_cloud = torch.empty(host.shape, dtype=torch.float32, device=s.device)
+            with torch.cuda.stream(s.stream):
+                s.dev_cloud.copy_(host, non_blocking=True)  # ordered behind this builder's previous exchange
+                s.staged.record(s.stream)
+            bs.wait_event(s.staged)
+            src = s.dev_cloud
+        bs.wait_event(s.xchg_done)  # this builder's tables and exchange buffer are free again
+        with torch.cuda.stream(bs):
+            m.uniformDivision(src)
+            m.create2DMap(demand, stream=bs.cuda_stream)
+            s.build_done.record(bs)
+        s.stream.wait_event(s.build_done)
+        with torch.cuda.stream(s.stream):
+            _check(m._h, L.gndt_xchg_run(m._h, s.stream.cuda_stream))
+            s.xchg_done.record(s.stream)
         self._inflight.append(s)
         return s
 
@@ -290,11 +330,15 @@ class TiledTwoDmap:
     def join(self):
         """Make the current stream wait for everything enqueued on the builders' streams."""
         cur = torch.cuda.current_stream(self.device)
+        if self.build_stream is not None:
+            cur.wait_stream(self.build_stream)
         for s in self.slots:
             if s.stream is not None:
                 cur.wait_stream(s.stream)
 
     def synchronize(self):
+        if self.build_stream is not None:
+            self.build_stream.synchronize()
         for s in self.slots:
             if s.stream is not None:
                 s.stream.synchronize()

@@ -24,7 +24,7 @@ rows = []
 
 def run(name, cloud, gl, zl, builds=a.builds):
     dev = torch.from_numpy(cloud).cuda()
-    m = TwoDmap(gl, zl); m.setInterval(0.08)
+    m = TwoDmap(gl, zl); m.setInterval(0.08); m.stage_timing(True)
     best = None
     for _ in range(builds):
         m.chatterCallback(dev, "slope"); torch.cuda.synchronize()
@@ -51,7 +51,7 @@ n3 = 50_000_000 if a.big else 20_000_000
 run(f"cfg3 terrain {n3 // 1_000_000}M", synthetic.cfg3(n3, extent=224.0 * (n3 / 50e6) ** 0.5), 0.1, 0.1, builds=4)
 
 # cfg4: streaming fusion of 100k-point scans into the resident cfg2 map
-m = TwoDmap(0.2, 0.1); m.setInterval(0.08)
+m = TwoDmap(0.2, 0.1); m.setInterval(0.08); m.stage_timing(True)
 m.chatterCallback(torch.from_numpy(cfg2).cuda(), "slope"); torch.cuda.synchronize()
 n_scans = 200
 lat_dev, lat_wall = [], []

@@ -23,6 +23,7 @@ if a.cfg in ("cfg3", "cfg5") and a.n != spec.n:
 cloud = torch.from_numpy(synthetic.make(a.cfg, a.n, **kw)).cuda()
 m = TwoDmap(a.grid or spec.grid_len, spec.z_len)
 m.setInterval(spec.slope_interval)
+m.stage_timing(True)
 for _ in range(a.builds):
     m.chatterCallback(cloud, "slope")
     torch.cuda.synchronize()
