@@ -12,7 +12,7 @@ REPO = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("GNDT_LIB") or os.path.join(HERE, "libgndt.so")  # GNDT_LIB: tuning variants only
 SOURCES = [os.path.join(HERE, "csrc", f) for f in (
     "gndt_api.cu", "gndt_device.cuh", "gndt_sort.cuh", "gndt_reduce.cuh", "gndt_label.cuh", "gndt_update.cuh",
-    "gndt_exchange.cuh", "gndt_graph.cuh")]
+    "gndt_exchange.cuh", "gndt_graph.cuh", "gndt_scan.cuh")]
 HEADER = os.path.join(REPO, "include", "gndt.h")
 LOOKUP_HEADER = os.path.join(REPO, "include", "gndt_lookup.h")
 

@@ -193,31 +193,6 @@ __device__ __forceinline__ void store_moments(VoxMoments *dst, u64 key, u32 firs
   for (int i = 0; i < 6; ++i) d[i] = q[i];
 }
 
-// Warp-wide decoupled look-back over one u32 word per tile: 32 predecessors per round trip.
-// Called by one full warp; the tile's own aggregate must already be published.
-__device__ __forceinline__ u32 warp_lookback_u32(u32 *state, int tile, u32 my_count, u32 *err) {
-  const int lane = threadIdx.x & 31;
-  u32 prefix = 0;
-  for (int hi = tile - 1; hi >= 0; hi -= 32) {
-    const int j = hi - lane;
-    u32 w = kFlagIncl;  // tiles before 0 count as an inclusive zero
-    if (j >= 0) {
-      u32 spins = 0;
-      do { w = ld_relaxed(state + j); } while ((w & kFlagMask) == 0 && ++spins < kSpinLimit);
-      if ((w & kFlagMask) == 0) { atomicOr(err, kErrWatchdog); w = kFlagIncl; }
-    }
-    const u32 incl = __ballot_sync(0xffffffffu, (w & kFlagIncl) != 0);
-    const int stop = incl ? __ffs(incl) - 1 : 31;  // nearest predecessor with an inclusive prefix
-    u32 v = (lane <= stop) ? (w & kValMask) : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    prefix += v;
-    if (incl) break;
-  }
-  if (lane == 0) st_relaxed(state + tile, kFlagIncl | (prefix + my_count));
-  return prefix;
-}
-
 // K3: one CTA per tile of 2048 sorted points -> raw moments of every voxel whose run starts
 // in the tile; partial runs at the tile edges go to the carry array.
 template <bool FAST>
