@@ -222,7 +222,8 @@ class TiledTwoDmap:
         if self.build_stream is None:
             self.build_stream = torch.cuda.Stream(s.device)
             for t in self.slots:
-                t.build_done, t.xchg_done, t.staged = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+                t.build_done, t.xchg_done, t.staged = torch.cuda.Event(enable_timing=True), torch.cuda.Event(), torch.cuda.Event()
+                t.build_start = torch.cuda.Event(enable_timing=True)
                 t.dev_cloud = None
         bs = self.build_stream
         cur = torch.cuda.current_stream(s.device)
@@ -240,6 +241,7 @@ class TiledTwoDmap:
             src = s.dev_cloud
         bs.wait_event(s.xchg_done)  # this builder's tables and exchange buffer are free again
         with torch.cuda.stream(bs):
+            s.build_start.record(bs)
             m.uniformDivision(src)
             m.create2DMap(demand, stream=bs.cuda_stream)
             s.build_done.record(bs)

@@ -12,6 +12,7 @@ cloud = torch.from_numpy(bench.make_cloud(rank)).cuda()
 origin = [float(np.float32(0.5 * bench.SCENE_W + 0.013)), float(np.float32(40.007)), 1.0]
 depth = int(os.environ.get("DEPTH", "3"))
 tm = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, depth=depth, gather=("slopes", "columns"), capacity=int(0.08 * 1e7 * world) + 1_000_000)
+build_ms = []
 def run(k):
     ahead = 0
     for i in range(k):
@@ -19,10 +20,12 @@ def run(k):
             tm.submit(cloud, "slope", origin=origin, cuts=None, filter_points=False); ahead += 1
         s = tm._inflight.popleft()
         s.xchg_done.synchronize()
+        build_ms.append(s.build_start.elapsed_time(s.build_done))
     tm.join()
 run(6); dist.barrier(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(30); e1.record(); torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / 30], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-if rank == 0: print(json.dumps({"world": world, "depth": depth, "skip": os.environ.get("GNDT_XCHG_SKIP", "0"), "spare": os.environ.get("GNDT_XCHG_SPARE", "24"), "ms_per_step": float(t.item())}), flush=True)
+bm = torch.zeros(world, device=dev); bm[rank] = float(np.mean(build_ms[-30:])); dist.all_reduce(bm)
+if rank == 0: print(json.dumps({"world": world, "depth": depth, "skip": os.environ.get("GNDT_XCHG_SKIP", "0"), "spare": os.environ.get("GNDT_XCHG_SPARE", "24"), "ms_per_step": round(float(t.item()), 4), "build_ms_per_rank": [round(float(x), 3) for x in bm.tolist()], "tma": os.environ.get("GNDT_XCHG_TMA", "0"), "reps": os.environ.get("GNDT_XCHG_REPS", "1"), "only": os.environ.get("GNDT_XCHG_ONLY_RANK", "-"), "ctas": os.environ.get("GNDT_XCHG_CTAS", "-")}), flush=True)
 dist.barrier(); dist.destroy_process_group()
