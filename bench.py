@@ -330,14 +330,25 @@ def main():
         cap = int(0.08 * n_pts * world) + 1_000_000  # voxels of the whole map (cfg2: 0.055 per point)
         gather = ("slopes", "columns")              # what the host planner reads (Cell / Slope, map2D.h:136-187)
         # DEPTH builders deep: the NVLink gather of build i overlaps the SM work of the next builds
-        tmp = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=DEPTH, gather=gather, capacity=cap)
-        tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=1, gather=gather, capacity=cap)  # one at a time
-        m = tm.map
+        pair = {}
+
+        def make(transport):
+            pair["tmp"] = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=DEPTH, gather=gather, capacity=cap, transport=transport)
+            pair["tm"] = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=1, gather=gather, capacity=cap, transport=transport)  # one at a time
+
+        def drop():
+            for k in ("tmp", "tm"):
+                if k in pair:
+                    try:
+                        pair.pop(k).close()
+                    except Exception:
+                        pass
 
         def step(src):
-            return tm.build(src, "slope", origin=origin, cuts=None, filter_points=False)
+            return pair["tm"].build(src, "slope", origin=origin, cuts=None, filter_points=False)
 
         def run_steps(src, k):
+            tmp = pair["tmp"]
             n_launch = 0
             ahead = 0
             for i in range(k):
@@ -348,6 +359,47 @@ def main():
                 n_launch += tmp.last_map.launch_count()
             tmp.join()
             return n_launch
+
+        def probe(transport, k=12):
+            """ms per pipelined step with this transport of the strip records (max over ranks), inf if any rank failed"""
+            ok, ms, why = 1.0, float("inf"), ""
+            try:
+                make(transport)
+                run_steps(resident, 4)
+                step(resident)
+                torch.cuda.synchronize()
+                dist.barrier()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record(); run_steps(resident, k); p1.record()
+                torch.cuda.synchronize()
+                ms = p0.elapsed_time(p1) / k
+            except Exception as e:  # e.g. the exchange watchdog: fall back to the other transport on EVERY rank
+                ok, why = 0.0, f"{type(e).__name__}: {e}"
+                print(f"[rank {rank}] transport {transport} failed: {why}", file=sys.stderr, flush=True)
+            t = torch.tensor([-ok, ms if ok else 0.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[1].item()) if t[0].item() == -1.0 else float("inf")
+
+        # which engine carries the strip records to the peers: the copy engines ("ce") or an SM kernel ("sm").
+        # Both are timed during warm-up; the faster one runs the timed region (GNDT_BENCH_TRANSPORT pins it).
+        forced = os.environ.get("GNDT_BENCH_TRANSPORT")
+        probes = {}
+        if forced:
+            make(forced)
+            chosen = forced
+        else:
+            for tr in ("sm", "ce"):
+                probes[tr] = probe(tr)
+                if tr == "sm":
+                    drop()
+            chosen = "ce"
+            if not probes["ce"] <= probes["sm"]:
+                drop()
+                chosen = "sm"
+                if probes["sm"] == float("inf"):
+                    raise RuntimeError("both exchange transports failed")
+                make("sm")
+        m = pair["tm"].map
     else:
         from grid_ndt_b200.pipeline import CloudPipeline
         m = TwoDmap(GRID_LEN, Z_LEN, device=local)  # one build at a time: stage times, latency, e2e serial
@@ -484,6 +536,8 @@ def main():
         e2e_mode = "CloudPipeline depth 2: H2D of cloud i+1 overlaps kernels + D2H of cloud i"
         pipe.close()
     else:
+        tmp = pair["tmp"]
+
         def piped(n):
             tmp.submit(host, "slope", origin=origin, cuts=None, filter_points=False)
             for i in range(n):
@@ -540,10 +594,13 @@ def main():
         "config": {"workload": WORKLOAD,
                    "points_per_gpu": n_pts, "voxels_per_gpu": v_tab, "columns_per_gpu": counts["n_columns"], "slopes_per_gpu": counts["n_slopes"],
                    "l2": "inputs (160 MB) and work buffers (320 MB) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": (f"x-strips x{world}: halo rows + gather of the Slope and Cell tables through peer-mapped memory (no NCCL on the data path); "
+                   "parallelism": (f"x-strips x{world}: halo rows + gather of the Slope and Cell tables through peer-mapped memory over NVLink (no NCCL on the data path); "
                                    if world > 1 else "single GPU; ")
                                   + (f"{DEPTH if world > 1 else 2} builds in flight on separate streams for `value`; value_latency / serial_ms_per_step = one build at a time"),
-                   "host": numa},
+                   "host": numa,
+                   **({"exchange": {"transport": chosen, "what": "ce = strip records carried to the peers by the copy engines (one 256-byte host round trip per build, "
+                                    "hidden behind the builds queued after it); sm = pushed by an SM kernel (no host round trip). Both timed during warm-up, the faster one kept",
+                                    "probe_ms_per_step": {k: (None if v == float("inf") else v) for k, v in probes.items()}}} if world > 1 else {})},
         "stage_ms": stages,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes": b_alg, "kernel_ms": t_build_ms,

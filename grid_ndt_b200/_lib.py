@@ -71,6 +71,9 @@ SYMBOLS = {
     "gndt_xchg_create": (_i, [_vp, _i, _i, _sz, _sz, _i, C.POINTER(XchgInfo)]),
     "gndt_xchg_connect": (_i, [_vp, C.POINTER(XchgInfo), _i]),
     "gndt_xchg_run": (_i, [_vp, _vp]),
+    "gndt_xchg_stage": (_i, [_vp, _vp]),
+    "gndt_xchg_counts_ready": (_i, [_vp]),
+    "gndt_xchg_send": (_i, [_vp, _vp]),
     "gndt_xchg_view_get": (_i, [_vp, C.POINTER(XchgView)]),
     "gndt_multi_create": (_i, [C.POINTER(Params), C.POINTER(C.c_int), _i, _sz, _sz, _i, C.POINTER(_vp)]),
     "gndt_multi_destroy": (_i, [_vp]),

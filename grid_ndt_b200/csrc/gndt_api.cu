@@ -102,6 +102,11 @@ struct gndt_handle {
   int x_push_ctas = 48;            // grid of the push kernel (GNDT_XCHG_CTAS), 256 threads each
   cudaStream_t x_stream = nullptr; // high-priority stream of the push: it takes the first slots that free up
   cudaEvent_t x_ev[2] = {};
+  // copy-engine transport (gndt_xchg_stage / gndt_xchg_send)
+  cudaStream_t x_copy[2] = {};     // the peer copies alternate between two streams (two engines busy)
+  cudaEvent_t x_ev_counts = nullptr, x_ev_copy = nullptr;
+  u32 *x_counts_host = nullptr;    // pinned: every strip's {voxels, columns, slopes, epoch} of the staged epoch
+  bool x_staged = false;
   u32 x_epoch = 0;
   bool x_created = false, x_connected = false;
   // state
@@ -519,6 +524,10 @@ int gndt_destroy(gndt_handle *h) {
   for (int r = 0; r < kMaxRanks; ++r)
     if (h->x_opened[r]) cudaIpcCloseMemHandle(h->x_opened[r]);
   if (h->x_stream) { cudaStreamDestroy(h->x_stream); for (int i = 0; i < 2; ++i) if (h->x_ev[i]) cudaEventDestroy(h->x_ev[i]); }
+  for (int i = 0; i < 2; ++i) if (h->x_copy[i]) cudaStreamDestroy(h->x_copy[i]);
+  if (h->x_ev_counts) cudaEventDestroy(h->x_ev_counts);
+  if (h->x_ev_copy) cudaEventDestroy(h->x_ev_copy);
+  if (h->x_counts_host) cudaFreeHost(h->x_counts_host);
   if (h->ring) { cudaFreeHost(h->ring); for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]); }
   Buffer *bufs[] = {&h->in_stage, &h->buf_a, &h->buf_b, &h->zero, &h->mom, &h->mom_alt, &h->table, &h->slopes,
                     &h->columns, &h->vfirst, &h->slope_col, &h->mom_scan, &h->upd_work, &h->msg_points, &h->small, &h->lookback, &h->f_zero, &h->xbuf, &h->g_work, &h->g_off, &h->g_tgt};
@@ -1032,7 +1041,12 @@ int gndt_xchg_create(gndt_handle *h, int rank, int world, size_t cap_records, si
     GNDT_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
     GNDT_CUDA(h, cudaStreamCreateWithPriority(&h->x_stream, cudaStreamNonBlocking, hi_p));
     for (int i = 0; i < 2; ++i) GNDT_CUDA(h, cudaEventCreateWithFlags(&h->x_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) GNDT_CUDA(h, cudaStreamCreateWithFlags(&h->x_copy[i], cudaStreamNonBlocking));
+    GNDT_CUDA(h, cudaEventCreateWithFlags(&h->x_ev_counts, cudaEventDisableTiming));
+    GNDT_CUDA(h, cudaEventCreateWithFlags(&h->x_ev_copy, cudaEventDisableTiming));
+    GNDT_CUDA(h, cudaHostAlloc(reinterpret_cast<void **>(&h->x_counts_host), kMaxRanks * 4 * sizeof(u32), cudaHostAllocDefault));
   }
+  h->x_staged = false;
   memset(mine, 0, sizeof(*mine));
   cudaIpcMemHandle_t ipc;
   GNDT_CUDA(h, cudaIpcGetMemHandle(&ipc, h->xbuf.p));
@@ -1082,40 +1096,148 @@ int gndt_xchg_connect(gndt_handle *h, const gndt_xchg_info *all, int world) {
   return GNDT_OK;
 }
 
-int gndt_xchg_run(gndt_handle *h, void *stream) {
-  if (!h) return GNDT_ERR_INVALID_ARG;
-  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
-  if (!h->x_connected) { h->err = "gndt_xchg_run: exchange not connected"; return GNDT_ERR_STATE; }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GNDT_CUDA(h, cudaSetDevice(h->device));
-  const u32 epoch = ++h->x_epoch;
+// publish -> halo rows -> boundary reach bits (everything of an exchange that needs no bulk transfer)
+static int xchg_front(gndt_handle *h, cudaStream_t st, u32 epoch, bool halo) {
   const XPeers &X = h->xp;
   const XLayout &L = h->xl;
   int *have = reinterpret_cast<int *>(static_cast<char *>(h->small.p) + 160);
-  u32 *done_counter = reinterpret_cast<u32 *>(static_cast<char *>(h->small.p) + 192);
   const DevParams dp = make_dev(h, h->params, h->cap_voxels);
   unsigned char *mine = X.buf[X.rank];
-  static const int skip = [] { const char *e = getenv("GNDT_XCHG_SKIP"); return e ? atoi(e) : 0; }();  // diagnosis only
-  if (skip & 4) return GNDT_OK;
   xchg_publish_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch);
-  if (!(skip & 1)) {
+  h->launches += 1;
+  if (!halo) return GNDT_OK;
   xchg_halo_send_kernel<<<2, 256, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_column *)h->columns.p, h->row_start,
                                            h->row_end, X, L, epoch);
   xchg_halo_wait_kernel<<<1, 32, 0, st>>>(h->ctl, X, L, epoch, have);
   xchg_halo_edges_kernel<<<grid_for(h, h->cap_voxels, 256, 4), 256, 0, st>>>(
       h->ctl, (gndt_voxel *)h->table.p, (gndt_slope *)h->slopes.p, reinterpret_cast<const gndt_voxel *>(mine + L.halo[0]),
       reinterpret_cast<const gndt_voxel *>(mine + L.halo[1]), have, dp);
-  }
+  h->launches += 3;
+  return GNDT_OK;
+}
+
+static int xchg_check(gndt_handle *h, const char *who) {
+  if (!h->built) { h->err = "no map has been built on this handle"; return GNDT_ERR_STATE; }
+  if (!h->x_connected) { h->err = std::string(who) + ": exchange not connected"; return GNDT_ERR_STATE; }
+  return GNDT_OK;
+}
+
+int gndt_xchg_run(gndt_handle *h, void *stream) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  int rc = xchg_check(h, "gndt_xchg_run");
+  if (rc != GNDT_OK) return rc;
+  if (h->x_staged) { h->err = "gndt_xchg_run: a staged exchange is waiting for gndt_xchg_send"; return GNDT_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  const u32 epoch = ++h->x_epoch;
+  const XPeers &X = h->xp;
+  const XLayout &L = h->xl;
+  u32 *done_counter = reinterpret_cast<u32 *>(static_cast<char *>(h->small.p) + 192);
+  static const int skip = [] { const char *e = getenv("GNDT_XCHG_SKIP"); return e ? atoi(e) : 0; }();  // diagnosis only
+  if (skip & 4) return GNDT_OK;
+  xchg_front(h, st, epoch, !(skip & 1));
   if (skip & 2) return GNDT_OK;
   // the bulk transfer and the final wait run on the high-priority stream, fenced by events on both sides
   GNDT_CUDA(h, cudaEventRecord(h->x_ev[0], st));
   GNDT_CUDA(h, cudaStreamWaitEvent(h->x_stream, h->x_ev[0], 0));
   xchg_push_kernel<<<h->x_push_ctas, kPushThreads, 0, h->x_stream>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_slope *)h->slopes.p,
-                                                            (const gndt_column *)h->columns.p, X, L, h->x_what, epoch, done_counter);
+                                                            (const gndt_column *)h->columns.p, X, L, h->x_what, epoch, done_counter, 0);
   xchg_wait_kernel<<<1, 32, 0, h->x_stream>>>(h->ctl, X, L, epoch);
   GNDT_CUDA(h, cudaEventRecord(h->x_ev[1], h->x_stream));
   GNDT_CUDA(h, cudaStreamWaitEvent(st, h->x_ev[1], 0));
-  h->launches += 6;
+  h->launches += 2;
+  h->counts_valid = false;
+  h->last_stream = st;
+  GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
+// ---- copy-engine transport: the same exchange with the bulk of the bytes moved by cudaMemcpyAsync ----
+// SM-issued stores to peers slow the build that runs beside them on the SENDING GPU (measured:
+// profiles/xchg_overlap_r2.md); copy-engine transfers do not.  The engines need sizes and addresses
+// on the host, so the exchange is split: gndt_xchg_stage enqueues everything up to the strip sitting,
+// indices made global, in this rank's own gathered tables, plus a 256-byte read-back of every strip's
+// counts; gndt_xchg_send waits for that read-back (the one host round trip; the next builds are
+// already queued behind it) and enqueues the peer copies, the `done` flags and the final wait.
+int gndt_xchg_stage(gndt_handle *h, void *stream) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  int rc = xchg_check(h, "gndt_xchg_stage");
+  if (rc != GNDT_OK) return rc;
+  if (h->x_staged) { h->err = "gndt_xchg_stage: the previous staged exchange has not been sent"; return GNDT_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  const u32 epoch = ++h->x_epoch;
+  const XPeers &X = h->xp;
+  const XLayout &L = h->xl;
+  u32 *done_counter = reinterpret_cast<u32 *>(static_cast<char *>(h->small.p) + 192);
+  xchg_front(h, st, epoch, true);  // its halo gate has seen every strip's counts of this epoch
+  xchg_push_kernel<<<h->x_push_ctas, kPushThreads, 0, st>>>(h->ctl, (const gndt_voxel *)h->table.p, (const gndt_slope *)h->slopes.p,
+                                                   (const gndt_column *)h->columns.p, X, L, h->x_what, epoch, done_counter, 1);
+  const XMail *mail = reinterpret_cast<const XMail *>(X.buf[X.rank] + L.mail);
+  GNDT_CUDA(h, cudaMemcpyAsync(h->x_counts_host, mail->counts[epoch & 1], kMaxRanks * 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+  GNDT_CUDA(h, cudaEventRecord(h->x_ev_counts, st));
+  h->launches += 1;
+  h->x_staged = true;
+  h->counts_valid = false;
+  h->last_stream = st;
+  GNDT_CUDA(h, cudaGetLastError());
+  return GNDT_OK;
+}
+
+int gndt_xchg_counts_ready(gndt_handle *h) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  if (!h->x_staged) return 0;
+  const cudaError_t e = cudaEventQuery(h->x_ev_counts);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  h->err = cudaGetErrorString(e);
+  return GNDT_ERR_CUDA;
+}
+
+int gndt_xchg_send(gndt_handle *h, void *stream) {
+  if (!h) return GNDT_ERR_INVALID_ARG;
+  if (!h->x_staged) { h->err = "gndt_xchg_send: nothing staged"; return GNDT_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GNDT_CUDA(h, cudaSetDevice(h->device));
+  GNDT_CUDA(h, cudaEventSynchronize(h->x_ev_counts));
+  h->x_staged = false;
+  const u32 epoch = h->x_epoch;
+  const XPeers &X = h->xp;
+  const XLayout &L = h->xl;
+  const int W = X.world;
+  uint64_t off[3] = {0, 0, 0}, total = 0;  // voxels, columns, slopes before this strip
+  for (int r = 0; r < W; ++r) {
+    const u32 *c = h->x_counts_host + 4 * r;
+    if (c[3] != epoch) { h->err = "gndt_xchg_send: strip " + std::to_string(r) + " never published its counts (watchdog)"; return GNDT_ERR_INTERNAL; }
+    if (r < X.rank) for (int k = 0; k < 3; ++k) off[k] += c[k];
+    total += c[0];
+  }
+  if (total > L.cap_records) { h->err = "gathered map exceeds the exchange capacity: " + std::to_string(total) + " > " + std::to_string(L.cap_records) + " records"; return GNDT_ERR_CAPACITY; }
+  const u32 *own = h->x_counts_host + 4 * X.rank;
+  struct { int bit; size_t base, rec; uint64_t first, n; } tab[3] = {
+      {GNDT_X_VOXELS, L.voxels, sizeof(gndt_voxel), off[0], own[0]},
+      {GNDT_X_SLOPES, L.slopes, sizeof(gndt_slope), off[2], own[2]},
+      {GNDT_X_COLUMNS, L.columns, sizeof(gndt_column), off[1], own[1]}};
+  for (int j = 0; j < 2; ++j) GNDT_CUDA(h, cudaStreamWaitEvent(h->x_copy[j], h->x_ev_counts, 0));
+  int n_copies = 0;
+  for (int d = 1; d < W; ++d) {  // start with the next rank: at any moment every GPU receives from one sender
+    const int p = (X.rank + d) % W;
+    for (const auto &t : tab) {
+      if (!(h->x_what & t.bit) || t.n == 0) continue;
+      const size_t at = t.base + (size_t)t.first * t.rec;
+      GNDT_CUDA(h, cudaMemcpyAsync(X.buf[p] + at, X.buf[X.rank] + at, (size_t)t.n * t.rec, cudaMemcpyDefault, h->x_copy[n_copies++ & 1]));
+    }
+  }
+  // flags and the final wait: high-priority stream (one warp each; they take the first free slot)
+  for (int j = 0; j < 2; ++j) {
+    GNDT_CUDA(h, cudaEventRecord(j ? h->x_ev_copy : h->x_ev[0], h->x_copy[j]));
+    GNDT_CUDA(h, cudaStreamWaitEvent(h->x_stream, j ? h->x_ev_copy : h->x_ev[0], 0));
+  }
+  xchg_done_kernel<<<1, 32, 0, h->x_stream>>>(X, L, epoch);
+  xchg_wait_kernel<<<1, 32, 0, h->x_stream>>>(h->ctl, X, L, epoch);
+  GNDT_CUDA(h, cudaEventRecord(h->x_ev[1], h->x_stream));
+  GNDT_CUDA(h, cudaStreamWaitEvent(st, h->x_ev[1], 0));
+  h->launches += 2;
   h->counts_valid = false;
   h->last_stream = st;
   GNDT_CUDA(h, cudaGetLastError());

@@ -206,7 +206,7 @@ xchg_halo_edges_kernel(Ctl *ctl, gndt_voxel *table, gndt_slope *slopes, const gn
 // leaves the SMs to the next build running beside it.
 template <int KIND>  // 0 voxels, 1 slopes, 2 columns
 __device__ __forceinline__ void push_table(const uint4 *src, size_t n_chunks, size_t dst_off_bytes, size_t first_chunk, const XPeers &X,
-                                           const u32 off[3]) {
+                                           const u32 off[3], int p_lo, int p_hi) {
   constexpr int kU = 8;
   constexpr u32 kPer = KIND == 0 ? 6u : (KIND == 1 ? 3u : 2u);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -225,7 +225,7 @@ __device__ __forceinline__ void push_table(const uint4 *src, size_t n_chunks, si
       if (KIND == 0) { if (part == 5) { v[u].z += off[1]; if (v[u].w != 0xFFFFFFFFu) v[u].w += off[2]; } }
       else if (KIND == 1) { if (part == 2) v[u].w += off[0]; }
       else { if (part == 0) v[u].w += off[0]; else v[u].y += off[2]; }
-      for (int p = 0; p < X.world; ++p) reinterpret_cast<uint4 *>(X.buf[p] + dst_off_bytes)[first_chunk + i] = v[u];
+      for (int p = p_lo; p < p_hi; ++p) reinterpret_cast<uint4 *>(X.buf[p] + dst_off_bytes)[first_chunk + i] = v[u];
     }
   }
 }
@@ -233,7 +233,7 @@ __device__ __forceinline__ void push_table(const uint4 *src, size_t n_chunks, si
 constexpr int kPushThreads = 256;  // small CTAs: they must fit beside a resident partition-pass CTA (half the register file)
 __global__ void __launch_bounds__(kPushThreads, 2)
 xchg_push_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_slope *slopes, const gndt_column *columns, XPeers X, XLayout L,
-                 int what, u32 epoch, u32 *done_counter) {
+                 int what, u32 epoch, u32 *done_counter, int local_only) {
   const XMail *mine = reinterpret_cast<const XMail *>(X.buf[X.rank] + L.mail);
   u32 off[3] = {0, 0, 0}, total[3] = {0, 0, 0};
   for (int r = 0; r < X.world; ++r)
@@ -246,11 +246,15 @@ xchg_push_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_slope *slopes, co
   const u32 nv = ld_sys(own + 0), nc = ld_sys(own + 1), ns = ld_sys(own + 2);
   const bool fits = total[0] <= L.cap_records;
   if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->err, kErrCapacity);
+  // local_only: this strip goes (indices made global) into the OWN gathered tables only; the copy engines
+  // carry it to the peers from there (gndt_xchg_send) and a separate kernel raises the `done` flags
+  const int p_lo = local_only ? X.rank : 0, p_hi = local_only ? X.rank + 1 : X.world;
   if (fits) {
-    if (what & 1) push_table<0>(reinterpret_cast<const uint4 *>(table), (size_t)nv * 6, L.voxels, (size_t)off[0] * 6, X, off);
-    if (what & 2) push_table<1>(reinterpret_cast<const uint4 *>(slopes), (size_t)ns * 3, L.slopes, (size_t)off[2] * 3, X, off);
-    if (what & 4) push_table<2>(reinterpret_cast<const uint4 *>(columns), (size_t)nc * 2, L.columns, (size_t)off[1] * 2, X, off);
+    if (what & 1) push_table<0>(reinterpret_cast<const uint4 *>(table), (size_t)nv * 6, L.voxels, (size_t)off[0] * 6, X, off, p_lo, p_hi);
+    if (what & 2) push_table<1>(reinterpret_cast<const uint4 *>(slopes), (size_t)ns * 3, L.slopes, (size_t)off[2] * 3, X, off, p_lo, p_hi);
+    if (what & 4) push_table<2>(reinterpret_cast<const uint4 *>(columns), (size_t)nc * 2, L.columns, (size_t)off[1] * 2, X, off, p_lo, p_hi);
   }
+  if (local_only) return;
   // completion: the last CTA to finish raises this strip's `done` flag in every mailbox
   __threadfence_system();
   __syncthreads();
@@ -262,6 +266,15 @@ xchg_push_kernel(Ctl *ctl, const gndt_voxel *table, const gndt_slope *slopes, co
       for (int p = 0; p < X.world; ++p) st_sys(&reinterpret_cast<XMail *>(X.buf[p] + L.mail)->done[epoch & 1][X.rank], epoch);
     }
   }
+}
+
+// X4c (copy-engine transport): the copies of this strip into every peer's tables have completed (stream order);
+// raise this strip's `done` flag in every mailbox.
+__global__ void xchg_done_kernel(XPeers X, XLayout L, u32 epoch) {
+  const int p = threadIdx.x;
+  if (p >= X.world) return;
+  __threadfence_system();
+  st_sys(&reinterpret_cast<XMail *>(X.buf[p] + L.mail)->done[epoch & 1][X.rank], epoch);
 }
 
 // X5: every strip has arrived in this rank's gathered tables.

@@ -84,13 +84,22 @@ class TiledTwoDmap:
 
     def __init__(self, res, zres, interval, rank: int, world: int, device: Optional[int] = None, group=None,
                  halo_records: int = 32768, depth: int = 1, exchange: str = "native", gather=("voxels", "slopes", "columns"),
-                 capacity: int = 8_000_000):
+                 capacity: int = 8_000_000, transport: Optional[str] = None):
         """exchange: "native" (peer-mapped memory inside libgndt.so) or "nccl" (point-to-point).
+        transport (native only): "ce" = the records travel by copy engine (gndt_xchg_stage / gndt_xchg_send: one
+        256-byte host round trip per build, hidden behind the builds already queued; does not slow the build
+        running beside it), "sm" = pushed by an SM kernel (gndt_xchg_run: no host round trip, but the build
+        beside it on the sending GPU slows down by about the duration of the push).  Default: "ce"
+        (GNDT_XCHG_TRANSPORT overrides).
         gather: which tables of the whole map every rank ends up with (native only; the planner reads
         slopes + columns).  capacity: voxels of the WHOLE map the gathered tables can hold (native)."""
         self.rank, self.world, self.group = rank, world, group
         self.halo_records = halo_records  # capacity of one halo row (records); overflow is reported, not truncated
         self.exchange = exchange if world > 1 else "nccl"  # one strip: nothing to exchange
+        import os
+        self.transport = transport or os.environ.get("GNDT_XCHG_TRANSPORT", "ce")
+        if self.transport not in ("ce", "sm"):
+            raise ValueError(f"transport {self.transport!r}: 'ce' or 'sm'")
         self.what = sum({"voxels": _abi.X_VOXELS, "slopes": _abi.X_SLOPES, "columns": _abi.X_COLUMNS}[g] for g in gather)
         self.slots = [_Slot(res, zres, interval, world, device, halo_records if self.exchange == "nccl" else 0, own_stream=depth > 1)
                       for _ in range(depth)]
@@ -188,7 +197,12 @@ class TiledTwoDmap:
                 m.create2DMap(demand, stream=st)
             if self.exchange == "native":
                 # halo rows, strip sizes, gather, index fix-up: all inside the library, all on this stream
-                _check(m._h, L.gndt_xchg_run(m._h, st))
+                if self.transport == "ce":
+                    _check(m._h, L.gndt_xchg_stage(m._h, st))
+                    _check(m._h, L.gndt_xchg_send(m._h, st))  # depth 1: nothing else to enqueue meanwhile
+                else:
+                    _check(m._h, L.gndt_xchg_run(m._h, st))
+                s.sent = True
                 self._inflight.append(s)
                 return s
             slot_b = (self.halo_records + 1) * REC
@@ -246,10 +260,46 @@ class TiledTwoDmap:
             m.create2DMap(demand, stream=bs.cuda_stream)
             s.build_done.record(bs)
         s.stream.wait_event(s.build_done)
+        if self.transport == "ce":
+            _check(m._h, L.gndt_xchg_stage(m._h, s.stream.cuda_stream))
+            s.sent = False
+            self._inflight.append(s)
+            self._send_ready()  # earlier builds whose counts have landed meanwhile
+            return s
         with torch.cuda.stream(s.stream):
             _check(m._h, L.gndt_xchg_run(m._h, s.stream.cuda_stream))
             s.xchg_done.record(s.stream)
+        s.sent = True
         self._inflight.append(s)
+        return s
+
+    def _send(self, s):
+        """Copy-engine transport, second half: blocks the host until the strip counts of build `s` are here."""
+        if getattr(s, "sent", True):
+            return
+        _check(s.map._h, lib().gndt_xchg_send(s.map._h, s.stream.cuda_stream))
+        s.xchg_done.record(s.stream)
+        s.sent = True
+
+    def _send_ready(self):
+        """Issue, in order and without blocking, the transfers of the builds in flight whose counts have landed."""
+        L = lib()
+        for s in self._inflight:
+            if getattr(s, "sent", True):
+                continue
+            rc = L.gndt_xchg_counts_ready(s.map._h)
+            _check(s.map._h, min(rc, 0))
+            if rc != 1:
+                break
+            self._send(s)
+
+    def wait_oldest(self):
+        """Pipelined native exchange: block until the oldest build in flight has been exchanged; returns its
+        builder WITHOUT reading sizes or tables (probes and benchmarks; collect() is the full form)."""
+        s = self._inflight.popleft()
+        self._send(s)
+        s.xchg_done.synchronize()
+        self._last = s
         return s
 
     # ---- phase 2: sizes on the host (the one synchronisation), records to every rank ---------
@@ -264,6 +314,8 @@ class TiledTwoDmap:
         m, L = s.map, lib()
         stream = s.stream if s.stream is not None else torch.cuda.current_stream(s.device)
         if self.exchange == "native":
+            self._send(s)
+            self._send_ready()
             v = XchgView()
             _check(m._h, L.gndt_xchg_view_get(m._h, C.byref(v)))  # synchronises this builder's stream only
             w = self.world
@@ -331,6 +383,8 @@ class TiledTwoDmap:
 
     def join(self):
         """Make the current stream wait for everything enqueued on the builders' streams."""
+        for s in self._inflight:
+            self._send(s)
         cur = torch.cuda.current_stream(self.device)
         if self.build_stream is not None:
             cur.wait_stream(self.build_stream)
@@ -339,6 +393,8 @@ class TiledTwoDmap:
                 cur.wait_stream(s.stream)
 
     def synchronize(self):
+        for s in self._inflight:
+            self._send(s)
         if self.build_stream is not None:
             self.build_stream.synchronize()
         for s in self.slots:

@@ -333,6 +333,20 @@ int gndt_xchg_create(gndt_handle *h, int rank, int world, size_t cap_records, si
                      gndt_xchg_info *mine);
 int gndt_xchg_connect(gndt_handle *h, const gndt_xchg_info *all, int world);
 int gndt_xchg_run(gndt_handle *h, void *stream);
+/*
+ * The same exchange with the bulk of the bytes carried by the copy engines instead of SM stores (the
+ * build that runs beside an SM push on the sending GPU loses about as much time as the push takes;
+ * copy-engine traffic does not disturb it: profiles/xchg_overlap_r2.md).  gndt_xchg_stage enqueues, on
+ * `stream`, everything up to this strip sitting in the rank's own gathered tables (indices global)
+ * and a 256-byte read-back of all strips' counts.  gndt_xchg_send blocks the HOST until that
+ * read-back has landed (one round trip; enqueue the next builds first), then enqueues the peer
+ * copies, the completion flags and the final wait, and makes `stream` wait for them.
+ * gndt_xchg_counts_ready: 1 if gndt_xchg_send would not block, 0 if it would, < 0 on error.
+ * gndt_xchg_view_get as after gndt_xchg_run.
+ */
+int gndt_xchg_stage(gndt_handle *h, void *stream);
+int gndt_xchg_counts_ready(gndt_handle *h);
+int gndt_xchg_send(gndt_handle *h, void *stream);
 /* Synchronises the exchange stream; fails with GNDT_ERR_CAPACITY if the map outgrew
  * cap_records / a row outgrew cap_halo_records, GNDT_ERR_INTERNAL if a peer never showed up. */
 int gndt_xchg_view_get(gndt_handle *h, gndt_xchg_view *out);

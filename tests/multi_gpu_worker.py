@@ -79,23 +79,28 @@ def main():
     ref_v, ref_s, ref_c = untiled(dev_cloud, origin)
 
     results = {}
-    for exchange in ("nccl", "native"):
-        tm = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, exchange=exchange, capacity=2_000_000)
+    # NCCL point-to-point, then the library's own exchange with the records pushed by an SM kernel ("sm")
+    # and carried by the copy engines ("ce", the default)
+    for name, exchange, transport in (("nccl", "nccl", None), ("native-sm", "native", "sm"), ("native", "native", "ce")):
+        tm = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, exchange=exchange, transport=transport, capacity=2_000_000)
         cuts = tm.plan(dev_cloud, origin=origin)
         assert cuts[0] == -32768 and cuts[-1] == 32768 and np.all(np.diff(cuts) >= 0)
         g = tm.build(dev_cloud, "slope", origin=origin, cuts=cuts, filter_points=True)
         got = tm.gathered_numpy()
         sizes = np.diff(g[1].astype(np.int64))
-        same_table(f"{exchange}: gathered voxels vs untiled build", got, ref_v)
+        same_table(f"{name}: gathered voxels vs untiled build", got, ref_v)
         if exchange == "native":
-            same_table("gathered slopes vs untiled build", tm.gathered_numpy("slopes"), ref_s)
-            same_table("gathered columns vs untiled build", tm.gathered_numpy("columns"), ref_c)
+            same_table(f"{name}: gathered slopes vs untiled build", tm.gathered_numpy("slopes"), ref_s)
+            same_table(f"{name}: gathered columns vs untiled build", tm.gathered_numpy("columns"), ref_c)
             if rank == 0:
-                check_against_oracle("strips " + exchange, tm, cloud, origin)
+                check_against_oracle("strips " + name, tm, cloud, origin)
                 assert sizes.min() > 0.5 * sizes.mean(), f"strips unbalanced: {sizes}"
-        results[exchange] = (tm, cuts, got)
+        results[name] = (tm, cuts, got)
         if rank == 0:
-            print(f"multi-gpu {exchange} ok: strips", sizes.tolist(), flush=True)
+            print(f"multi-gpu {name} ok: strips", sizes.tolist(), flush=True)
+    # the two transports must deliver the same bytes
+    for which in ("voxels", "slopes", "columns"):
+        assert results["native"][0].gathered_numpy(which).tobytes() == results["native-sm"][0].gathered_numpy(which).tobytes(), which
     tm, cuts, got = results["native"]
 
     # empty strips (ADVICE: equal cuts used to mean "filter off"): rank 0 gets nothing; with >= 3 ranks
@@ -119,16 +124,19 @@ def main():
     cuts_b = tm.plan(dev_b, origin=origin_b)
     tm.build(dev_b, "slope", origin=origin_b, cuts=cuts_b, filter_points=True)
     got_b = tm.gathered_numpy().copy()
-    tm2 = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, depth=2, capacity=2_000_000)
-    for rep in range(2):
-        tm2.submit(dev_cloud, "slope", origin=origin, cuts=cuts, filter_points=True)
-        tm2.submit(dev_b, "slope", origin=origin_b, cuts=cuts_b, filter_points=True)
-        ta, _ = tm2.collect()
-        ta = ta.cpu().numpy().tobytes()
-        tb, _ = tm2.collect()
-        tb = tb.cpu().numpy().tobytes()
-        assert ta == got.tobytes(), f"pipelined build A differs (rep {rep})"  # same strips, same tiles: bytes
-        assert tb == got_b.tobytes(), f"pipelined build B differs (rep {rep})"
+    pipelined = []
+    for transport in ("ce", "sm"):
+        tm2 = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, depth=2, capacity=2_000_000, transport=transport)
+        pipelined.append(tm2)
+        for rep in range(2):
+            tm2.submit(dev_cloud, "slope", origin=origin, cuts=cuts, filter_points=True)
+            tm2.submit(dev_b, "slope", origin=origin_b, cuts=cuts_b, filter_points=True)
+            ta, _ = tm2.collect()
+            ta = ta.cpu().numpy().tobytes()
+            tb, _ = tm2.collect()
+            tb = tb.cpu().numpy().tobytes()
+            assert ta == got.tobytes(), f"pipelined build A differs ({transport}, rep {rep})"  # same strips, same tiles: bytes
+            assert tb == got_b.tobytes(), f"pipelined build B differs ({transport}, rep {rep})"
     if rank == 0:
         print("multi-gpu pipelined ok", flush=True)
 
@@ -147,7 +155,7 @@ def main():
         check_against_oracle("streamed strips", tm3, cloud, origin)
     tm3.close()
     dist.barrier()
-    for t in (results["native"][0], results["nccl"][0], tm2):
+    for t in [r[0] for r in results.values()] + pipelined:
         t.close()
     dist.destroy_process_group()
 

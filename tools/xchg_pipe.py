@@ -11,15 +11,14 @@ dist.init_process_group("nccl", device_id=dev)
 cloud = torch.from_numpy(bench.make_cloud(rank)).cuda()
 origin = [float(np.float32(0.5 * bench.SCENE_W + 0.013)), float(np.float32(40.007)), 1.0]
 depth = int(os.environ.get("DEPTH", "3"))
-tm = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, depth=depth, gather=("slopes", "columns"), capacity=int(0.08 * 1e7 * world) + 1_000_000)
+tm = TiledTwoDmap(0.2, 0.1, 0.08, rank, world, device=local, depth=depth, transport=os.environ.get("TRANSPORT"), gather=("slopes", "columns"), capacity=int(0.08 * 1e7 * world) + 1_000_000)
 build_ms = []
 def run(k):
     ahead = 0
     for i in range(k):
         while ahead < min(k, i + tm.depth):
             tm.submit(cloud, "slope", origin=origin, cuts=None, filter_points=False); ahead += 1
-        s = tm._inflight.popleft()
-        s.xchg_done.synchronize()
+        s = tm.wait_oldest()
         build_ms.append(s.build_start.elapsed_time(s.build_done))
     tm.join()
 run(6); dist.barrier(); torch.cuda.synchronize()
@@ -27,5 +26,5 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(30); e1.record(); torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / 30], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 bm = torch.zeros(world, device=dev); bm[rank] = float(np.mean(build_ms[-30:])); dist.all_reduce(bm)
-if rank == 0: print(json.dumps({"world": world, "depth": depth, "skip": os.environ.get("GNDT_XCHG_SKIP", "0"), "spare": os.environ.get("GNDT_XCHG_SPARE", "24"), "ms_per_step": round(float(t.item()), 4), "build_ms_per_rank": [round(float(x), 3) for x in bm.tolist()], "tma": os.environ.get("GNDT_XCHG_TMA", "0"), "reps": os.environ.get("GNDT_XCHG_REPS", "1"), "only": os.environ.get("GNDT_XCHG_ONLY_RANK", "-"), "ctas": os.environ.get("GNDT_XCHG_CTAS", "-")}), flush=True)
+if rank == 0: print(json.dumps({"world": world, "depth": depth, "transport": tm.transport, "skip": os.environ.get("GNDT_XCHG_SKIP", "0"), "ms_per_step": round(float(t.item()), 4), "build_ms_per_rank": [round(float(x), 3) for x in bm.tolist()]}), flush=True)
 dist.barrier(); dist.destroy_process_group()
