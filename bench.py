@@ -198,7 +198,7 @@ def run_reference(args):
     return 0
 
 
-def multi_gpu_parity(rank, world, local):
+def multi_gpu_parity(rank, world, local, transport=None):
     """Outside the timed region: one 2 M-point cloud cut into `world` strips, built, exchanged,
     and (rank 0) compared with the oracle to the full parity bar (tests/parity.py)."""
     import torch
@@ -208,7 +208,7 @@ def multi_gpu_parity(rank, world, local):
     cloud = synthetic.cfg2(2_000_000, scale=0.2 ** 0.5)
     origin = [float(v) for v in cloud[0, :3]]
     dev_cloud = torch.from_numpy(cloud).cuda()
-    tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, capacity=3_000_000)
+    tm = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, capacity=3_000_000, transport=transport)
     cuts = tm.plan(dev_cloud, origin=origin)
     tm.build(dev_cloud, "slope", origin=origin, cuts=cuts, filter_points=True)
     out = None
@@ -232,7 +232,7 @@ def multi_gpu_parity(rank, world, local):
     return out
 
 
-def target_cfg3(rank, world, local, dev, peak):
+def target_cfg3(rank, world, local, dev, peak, transport=None):
     """North star: ONE cloud (cfg3 terrain, 50 M points, 0.1 m cells) strong-scaled over the N
     strips, whole map (Slope + Cell tables) gathered on every GPU; cloud resident in HBM."""
     import torch
@@ -244,7 +244,7 @@ def target_cfg3(rank, world, local, dev, peak):
     origin = [float(v) for v in cloud[0, :3]]
     full = torch.from_numpy(cloud).cuda()
     tm = TiledTwoDmap(0.1, 0.1, INTERVAL, rank, world, device=local, halo_records=65536, gather=("slopes", "columns"),
-                      capacity=int(0.2 * n) + 1_000_000)
+                      capacity=int(0.2 * n) + 1_000_000, transport=transport)
     cuts = tm.plan(full, origin=origin)
     rows = {}
     for mode in ("full", "share"):
@@ -330,19 +330,18 @@ def main():
         cap = int(0.08 * n_pts * world) + 1_000_000  # voxels of the whole map (cfg2: 0.055 per point)
         gather = ("slopes", "columns")              # what the host planner reads (Cell / Slope, map2D.h:136-187)
         # DEPTH builders deep: the NVLink gather of build i overlaps the SM work of the next builds
-        pair = {}
+        pair, parked = {}, []
 
         def make(transport):
             pair["tmp"] = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=DEPTH, gather=gather, capacity=cap, transport=transport)
             pair["tm"] = TiledTwoDmap(GRID_LEN, Z_LEN, INTERVAL, rank, world, device=local, depth=1, gather=gather, capacity=cap, transport=transport)  # one at a time
 
-        def drop():
+        def park():
+            """Set the current builders aside WITHOUT freeing them: their exchange buffers are mapped by the peers
+            (an exported buffer must outlive the peers' mappings), so everything is closed together at the end."""
             for k in ("tmp", "tm"):
                 if k in pair:
-                    try:
-                        pair.pop(k).close()
-                    except Exception:
-                        pass
+                    parked.append(pair.pop(k))
 
         def step(src):
             return pair["tm"].build(src, "slope", origin=origin, cuts=None, filter_points=False)
@@ -367,8 +366,7 @@ def main():
                 make(transport)
                 run_steps(resident, 4)
                 step(resident)
-                torch.cuda.synchronize()
-                dist.barrier()
+                torch.cuda.synchronize()  # no collective inside the try: a rank that fails must still meet the others below
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record(); run_steps(resident, k); p1.record()
                 torch.cuda.synchronize()
@@ -388,17 +386,15 @@ def main():
             make(forced)
             chosen = forced
         else:
+            kept = {}
             for tr in ("sm", "ce"):
                 probes[tr] = probe(tr)
-                if tr == "sm":
-                    drop()
-            chosen = "ce"
-            if not probes["ce"] <= probes["sm"]:
-                drop()
-                chosen = "sm"
-                if probes["sm"] == float("inf"):
-                    raise RuntimeError("both exchange transports failed")
-                make("sm")
+                kept[tr] = dict(pair)
+                park()
+            if probes["ce"] == probes["sm"] == float("inf"):
+                raise RuntimeError("both exchange transports failed")
+            chosen = "ce" if probes["ce"] <= probes["sm"] else "sm"
+            pair.update(kept[chosen])
         m = pair["tm"].map
     else:
         from grid_ndt_b200.pipeline import CloudPipeline
@@ -616,7 +612,7 @@ def main():
         "clocks": clk.summary(),
     }
     if world > 1 and not args.no_extras:
-        par = multi_gpu_parity(rank, world, local)
+        par = multi_gpu_parity(rank, world, local, chosen)  # the transport that ran the timed region
         bad = torch.tensor([0 if (par is None or (par["ok"] and par["unexplained"] == 0)) else 1], device=dev)
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
         line["parity"] = par
@@ -626,7 +622,7 @@ def main():
             dist.destroy_process_group()
             return 1
         if TARGET_POINTS:
-            line["target_cfg3"] = target_cfg3(rank, world, local, dev, peak)
+            line["target_cfg3"] = target_cfg3(rank, world, local, dev, peak, chosen)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from grid_ndt_b200._abi import default_params
         from oracle import oracle as O
