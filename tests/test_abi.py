@@ -117,3 +117,8 @@ def test_create_rejects_bad_params():
     assert L.gndt_create(None, 0, C.byref(h)) == _abi.GNDT_ERR_INVALID_ARG
     assert L.gndt_build(None, None, 0, 16, 0, None) == _abi.GNDT_ERR_INVALID_ARG
     assert L.gndt_counts(None, None) == _abi.GNDT_ERR_INVALID_ARG
+    # the strip exchange (both transports) refuses a missing handle before touching the device
+    for name in ("gndt_xchg_run", "gndt_xchg_stage", "gndt_xchg_send"):
+        assert getattr(L, name)(None, None) == _abi.GNDT_ERR_INVALID_ARG, name
+    assert L.gndt_xchg_counts_ready(None) == _abi.GNDT_ERR_INVALID_ARG
+    assert L.gndt_xchg_view_get(None, None) == _abi.GNDT_ERR_INVALID_ARG
